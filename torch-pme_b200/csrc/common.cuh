@@ -1,0 +1,72 @@
+// Shared device/host helpers for the sm_100a PME/P3M kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#define TPME_P3M 0
+#define TPME_LAGRANGE 1
+
+namespace tpme {
+
+// ---- error plumbing (C ABI returns int; the message is kept per thread) ---------------
+void set_last_error(const char* where, const char* what);
+
+#define TPME_CUDA_OK(expr)                                              \
+  do {                                                                  \
+    cudaError_t err__ = (expr);                                         \
+    if (err__ != cudaSuccess) {                                         \
+      ::tpme::set_last_error(#expr, cudaGetErrorString(err__));         \
+      return 100 + (int)err__;                                          \
+    }                                                                   \
+  } while (0)
+
+#define TPME_REQUIRE(cond, msg)                                         \
+  do {                                                                  \
+    if (!(cond)) {                                                      \
+      ::tpme::set_last_error(#cond, msg);                               \
+      return 1;                                                         \
+    }                                                                   \
+  } while (0)
+
+// ---- small math helpers --------------------------------------------------------------
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+
+template <typename T> struct Mat3 { T m[9]; };  // row-major, passed by value to kernels
+
+template <typename T>
+__host__ inline Mat3<T> load_mat3(const double* host9) {
+  Mat3<T> out;
+  for (int i = 0; i < 9; ++i) out.m[i] = (T)host9[i];
+  return out;
+}
+
+// non-negative modulo for possibly negative i (atoms may sit outside the cell;
+// reference: ``(idx + i) % ns`` in lib/mesh_interpolator.py:352)
+__device__ __forceinline__ int wrap_index(int i, int n) {
+  int r = i % n;
+  return r < 0 ? r + n : r;
+}
+
+__device__ __forceinline__ float floor_t(float x) { return floorf(x); }
+__device__ __forceinline__ double floor_t(double x) { return floor(x); }
+__device__ __forceinline__ float rint_t(float x) { return rintf(x); }   // ties-to-even == torch.round
+__device__ __forceinline__ double rint_t(double x) { return rint(x); }
+
+// native reduction atomics (no return value -> RED.E.ADD in SASS)
+__device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }
+
+inline int num_sms() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+
+}  // namespace tpme

@@ -1,0 +1,343 @@
+// Mesh interpolation kernels: charge spreading (points -> mesh) and potential / force
+// gathering (mesh -> points) for P3M (n = 1..5) and Lagrange (n = 3..7) stencils.
+//
+// Replaces the (n^3, N) index/weight tensors and index_put_/fancy-index ops of
+// src/torchpme/lib/mesh_interpolator.py:303-457 with in-register stencils.
+#include "common.cuh"
+#include "stencil_weights.cuh"
+#include "../../include/torchpme_b200.h"
+
+namespace tpme {
+
+// Fractional mesh coordinate, stencil base index and 1-D weights of one point.
+//   u = r @ r2u                                   (mesh_interpolator.py:326)
+//   even n: i0 = floor(u), x = u - (i0 + 1/2);  odd n: i0 = rint(u), x = u - i0   (:329-341)
+//   first node index = i0 + 1 - (n + 1) / 2                                        (:350-359)
+template <typename T, int METHOD, int N, bool DERIV>
+__device__ __forceinline__ void point_stencil(const T* __restrict__ pos, const Mat3<T>& r2u,
+                                              int (&first)[3], T (&w)[3][N], T (&dw)[3][N]) {
+  const T r0 = pos[0], r1 = pos[1], r2 = pos[2];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const T u = r0 * r2u.m[a] + r1 * r2u.m[3 + a] + r2 * r2u.m[6 + a];
+    T base, x;
+    if (N % 2 == 0) {
+      base = floor_t(u);
+      x = u - (base + T(0.5));
+    } else {
+      base = rint_t(u);
+      x = u - base;
+    }
+    first[a] = (int)base + 1 - (N + 1) / 2;
+    Stencil<METHOD, N>::template eval<T, DERIV>(x, w[a], dw[a]);
+  }
+}
+
+template <typename T, int N>
+__device__ __forceinline__ T pick(const T (&arr)[N], int k) {
+  T out = arr[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) out = (i == k) ? arr[i] : out;
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------
+// spread: one thread per (point, a, b) stencil column; the z-run of N nodes is contiguous.
+// ---------------------------------------------------------------------------------------
+template <typename T, int METHOD, int N>
+__global__ void __launch_bounds__(256)
+spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, int64_t n_points,
+              int n_channels, Mat3<T> r2u, int nx, int ny, int nz, T* __restrict__ mesh) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t point = tid / (N * N);
+  if (point >= n_points) return;
+  const int ab = (int)(tid - point * (N * N));
+  const int a = ab / N, b = ab - a * N;
+
+  int first[3];
+  T w[3][N], dw[3][N];
+  point_stencil<T, METHOD, N, false>(positions + 3 * point, r2u, first, w, dw);
+
+  const int ix = wrap_index(first[0] + a, nx);
+  const int iy = wrap_index(first[1] + b, ny);
+  const T wxy = pick<T, N>(w[0], a) * pick<T, N>(w[1], b);
+  const int64_t row = ((int64_t)ix * ny + iy) * nz;
+  const int64_t mesh_size = (int64_t)nx * ny * nz;
+  int iz = wrap_index(first[2], nz);
+  for (int ch = 0; ch < n_channels; ++ch) {
+    const T q = weights[point * n_channels + ch] * wxy;
+    T* dst = mesh + ch * mesh_size + row;
+    int z = iz;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      red_add(dst + z, q * w[2][c]);
+      z = (z + 1 == nz) ? 0 : z + 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// gather: a group of G lanes per point, lanes own (a, b) stencil columns, shuffle-reduce.
+//   MODE bit 0: values, bit 1: dvalues/dr, bit 2: vjp into grad_positions (+ grad_r2u)
+// ---------------------------------------------------------------------------------------
+template <int N> struct GroupSize {
+  static constexpr int value = (N * N <= 1) ? 1 : (N * N <= 4) ? 4 : (N * N <= 16) ? 16 : 32;
+};
+
+template <typename T, int METHOD, int N, int MODE>
+__global__ void __launch_bounds__(256)
+gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
+              const T* __restrict__ coef, int64_t n_points, int n_channels, Mat3<T> r2u, int nx,
+              int ny, int nz, T* __restrict__ values, T* __restrict__ dvalues,
+              T* __restrict__ grad_positions, int accumulate, T* __restrict__ grad_r2u) {
+  constexpr int G = GroupSize<N>::value;
+  constexpr bool DERIV = (MODE & 6) != 0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t point_raw = tid / G;
+  const bool valid = point_raw < n_points;
+  const int64_t point = valid ? point_raw : n_points - 1;
+  const int lane = (int)(tid % G);
+
+  int first[3];
+  T w[3][N], dw[3][N];
+  point_stencil<T, METHOD, N, DERIV>(positions + 3 * point, r2u, first, w, dw);
+  const int iz0 = wrap_index(first[2], nz);
+  const int64_t mesh_size = (int64_t)nx * ny * nz;
+
+  T gu[3] = {T(0), T(0), T(0)};  // vjp accumulator in mesh coordinates
+  for (int ch = 0; ch < n_channels; ++ch) {
+    T val = T(0), du0 = T(0), du1 = T(0), du2 = T(0);
+    const T* src_ch = mesh + ch * mesh_size;
+    for (int ab = lane; ab < N * N; ab += G) {
+      const int a = ab / N, b = ab - a * N;
+      const int ix = wrap_index(first[0] + a, nx);
+      const int iy = wrap_index(first[1] + b, ny);
+      const T* src = src_ch + ((int64_t)ix * ny + iy) * nz;
+      T s = T(0), sd = T(0);
+      int z = iz0;
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        const T v = __ldg(src + z);
+        s = fma_t(v, w[2][c], s);
+        if (DERIV) sd = fma_t(v, dw[2][c], sd);
+        z = (z + 1 == nz) ? 0 : z + 1;
+      }
+      const T wa = pick<T, N>(w[0], a), wb = pick<T, N>(w[1], b);
+      val = fma_t(wa * wb, s, val);
+      if (DERIV) {
+        du0 = fma_t(pick<T, N>(dw[0], a) * wb, s, du0);
+        du1 = fma_t(wa * pick<T, N>(dw[1], b), s, du1);
+        du2 = fma_t(wa * wb, sd, du2);
+      }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+      val += __shfl_xor_sync(0xffffffffu, val, off, G);
+      if (DERIV) {
+        du0 += __shfl_xor_sync(0xffffffffu, du0, off, G);
+        du1 += __shfl_xor_sync(0xffffffffu, du1, off, G);
+        du2 += __shfl_xor_sync(0xffffffffu, du2, off, G);
+      }
+    }
+    if (lane == 0 && valid) {
+      if (MODE & 1) values[point * n_channels + ch] = val;
+      if (MODE & 2) {
+        T* out = dvalues + (point * n_channels + ch) * 3;
+#pragma unroll
+        for (int b = 0; b < 3; ++b)  // du_a/dr_b = r2u[b][a]
+          out[b] = r2u.m[3 * b] * du0 + r2u.m[3 * b + 1] * du1 + r2u.m[3 * b + 2] * du2;
+      }
+      if (MODE & 4) {
+        const T cf = coef[point * n_channels + ch];
+        gu[0] = fma_t(cf, du0, gu[0]);
+        gu[1] = fma_t(cf, du1, gu[1]);
+        gu[2] = fma_t(cf, du2, gu[2]);
+      }
+    }
+  }
+  if (MODE & 4) {
+    if (lane == 0 && valid) {
+      T* out = grad_positions + 3 * point;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const T g = r2u.m[3 * b] * gu[0] + r2u.m[3 * b + 1] * gu[1] + r2u.m[3 * b + 2] * gu[2];
+        out[b] = accumulate ? out[b] + g : g;
+      }
+    }
+    if (grad_r2u != nullptr) {  // block-uniform branch
+      __shared__ T red[9][8];
+      const bool lead = (lane == 0 && valid);
+      const T r[3] = {positions[3 * point], positions[3 * point + 1], positions[3 * point + 2]};
+      const int warp = threadIdx.x >> 5, wl = threadIdx.x & 31;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        T v = lead ? r[e / 3] * gu[e % 3] : T(0);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (wl == 0) red[e][warp] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < 9) {
+        T v = T(0);
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) v += red[threadIdx.x][k];
+        red_add(grad_r2u + threadIdx.x, v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------
+template <typename T, int METHOD, int N>
+int launch_spread(const void* positions, const void* weights, int64_t n_points, int n_channels,
+                  const double* r2u, int nx, int ny, int nz, void* mesh, cudaStream_t stream) {
+  const int64_t threads = n_points * N * N;
+  const int block = 256;
+  const int64_t grid = (threads + block - 1) / block;
+  if (grid == 0) return 0;
+  spread_kernel<T, METHOD, N><<<(unsigned)grid, block, 0, stream>>>(
+      (const T*)positions, (const T*)weights, n_points, n_channels, load_mat3<T>(r2u), nx, ny, nz,
+      (T*)mesh);
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, int METHOD, int N, int MODE>
+int launch_gather(const void* mesh, const void* positions, const void* coef, int64_t n_points,
+                  int n_channels, const double* r2u, int nx, int ny, int nz, void* values,
+                  void* dvalues, void* grad_positions, int accumulate, void* grad_r2u,
+                  cudaStream_t stream) {
+  constexpr int G = GroupSize<N>::value;
+  const int64_t threads = n_points * G;
+  const int block = 256;
+  const int64_t grid = (threads + block - 1) / block;
+  if (grid == 0) return 0;
+  gather_kernel<T, METHOD, N, MODE><<<(unsigned)grid, block, 0, stream>>>(
+      (const T*)mesh, (const T*)positions, (const T*)coef, n_points, n_channels,
+      load_mat3<T>(r2u), nx, ny, nz, (T*)values, (T*)dvalues, (T*)grad_positions, accumulate,
+      (T*)grad_r2u);
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+#define TPME_DISPATCH_STENCIL(CALL)                                         \
+  if (method == TPME_P3M) {                                                 \
+    switch (nodes) {                                                        \
+      case 1: return CALL(TPME_P3M, 1);                                     \
+      case 2: return CALL(TPME_P3M, 2);                                     \
+      case 3: return CALL(TPME_P3M, 3);                                     \
+      case 4: return CALL(TPME_P3M, 4);                                     \
+      case 5: return CALL(TPME_P3M, 5);                                     \
+    }                                                                       \
+  } else if (method == TPME_LAGRANGE) {                                     \
+    switch (nodes) {                                                        \
+      case 3: return CALL(TPME_LAGRANGE, 3);                                \
+      case 4: return CALL(TPME_LAGRANGE, 4);                                \
+      case 5: return CALL(TPME_LAGRANGE, 5);                                \
+      case 6: return CALL(TPME_LAGRANGE, 6);                                \
+      case 7: return CALL(TPME_LAGRANGE, 7);                                \
+    }                                                                       \
+  }                                                                         \
+  set_last_error("stencil", "unsupported (method, interpolation_nodes) pair"); \
+  return 2;
+
+template <typename T>
+int spread_dispatch(const void* positions, const void* weights, int64_t n_points, int n_channels,
+                    const double* r2u, int nx, int ny, int nz, int nodes, int method, void* mesh,
+                    cudaStream_t stream) {
+#define CALL(M, N) \
+  launch_spread<T, M, N>(positions, weights, n_points, n_channels, r2u, nx, ny, nz, mesh, stream)
+  TPME_DISPATCH_STENCIL(CALL)
+#undef CALL
+}
+
+template <typename T, int MODE>
+int gather_dispatch(const void* mesh, const void* positions, const void* coef, int64_t n_points,
+                    int n_channels, const double* r2u, int nx, int ny, int nz, int nodes,
+                    int method, void* values, void* dvalues, void* grad_positions, int accumulate,
+                    void* grad_r2u, cudaStream_t stream) {
+#define CALL(M, N)                                                                              \
+  launch_gather<T, M, N, MODE>(mesh, positions, coef, n_points, n_channels, r2u, nx, ny, nz,   \
+                               values, dvalues, grad_positions, accumulate, grad_r2u, stream)
+  TPME_DISPATCH_STENCIL(CALL)
+#undef CALL
+}
+
+static int check_mesh_args(int dtype, int nx, int ny, int nz, int n_channels, int64_t n_points) {
+  TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (float32) or 1 (float64)");
+  TPME_REQUIRE(nx > 0 && ny > 0 && nz > 0, "mesh dimensions must be positive");
+  TPME_REQUIRE(n_channels >= 0 && n_points >= 0, "negative sizes");
+  return 0;
+}
+
+}  // namespace tpme
+
+using namespace tpme;
+
+extern "C" int tpme_spread(int dtype, const void* positions, const void* weights,
+                           int64_t n_points, int n_channels, const double* r2u_host, int nx,
+                           int ny, int nz, int nodes, int method, void* mesh, int accumulate,
+                           void* stream) {
+  if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t elem = dtype == 0 ? 4 : 8;
+  if (!accumulate)
+    TPME_CUDA_OK(cudaMemsetAsync(mesh, 0, elem * (size_t)n_channels * nx * ny * nz, s));
+  if (n_points == 0 || n_channels == 0) return 0;
+  if (dtype == 0)
+    return spread_dispatch<float>(positions, weights, n_points, n_channels, r2u_host, nx, ny, nz,
+                                  nodes, method, mesh, s);
+  return spread_dispatch<double>(positions, weights, n_points, n_channels, r2u_host, nx, ny, nz,
+                                 nodes, method, mesh, s);
+}
+
+extern "C" int tpme_gather(int dtype, const void* mesh, const void* positions, int64_t n_points,
+                           int n_channels, const double* r2u_host, int nx, int ny, int nz,
+                           int nodes, int method, void* values, void* dvalues, void* stream) {
+  if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
+  TPME_REQUIRE(values != nullptr || dvalues != nullptr, "nothing to compute");
+  if (n_points == 0 || n_channels == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int mode = (values ? 1 : 0) | (dvalues ? 2 : 0);
+#define GO(T, MODE)                                                                          \
+  return gather_dispatch<T, MODE>(mesh, positions, nullptr, n_points, n_channels, r2u_host,  \
+                                  nx, ny, nz, nodes, method, values, dvalues, nullptr, 0,    \
+                                  nullptr, s)
+  if (dtype == 0) {
+    if (mode == 1) GO(float, 1);
+    if (mode == 2) GO(float, 2);
+    GO(float, 3);
+  }
+  if (mode == 1) GO(double, 1);
+  if (mode == 2) GO(double, 2);
+  GO(double, 3);
+#undef GO
+}
+
+extern "C" int tpme_gather_vjp(int dtype, const void* mesh, const void* positions,
+                               const void* coef, int64_t n_points, int n_channels,
+                               const double* r2u_host, int nx, int ny, int nz, int nodes,
+                               int method, void* grad_positions, void* values, int accumulate,
+                               void* grad_r2u, void* stream) {
+  if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
+  TPME_REQUIRE(grad_positions != nullptr && coef != nullptr, "grad_positions / coef missing");
+  if (n_points == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_channels == 0) {
+    if (!accumulate)
+      TPME_CUDA_OK(cudaMemsetAsync(grad_positions, 0, (dtype ? 8 : 4) * 3 * (size_t)n_points, s));
+    return 0;
+  }
+#define GO(T, MODE)                                                                           \
+  return gather_dispatch<T, MODE>(mesh, positions, coef, n_points, n_channels, r2u_host, nx,  \
+                                  ny, nz, nodes, method, values, nullptr, grad_positions,     \
+                                  accumulate, grad_r2u, s)
+  if (dtype == 0) {
+    if (values) GO(float, 5);
+    GO(float, 4);
+  }
+  if (values) GO(double, 5);
+  GO(double, 4);
+#undef GO
+}

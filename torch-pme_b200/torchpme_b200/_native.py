@@ -1,0 +1,378 @@
+"""
+ctypes binding of ``libtorchpme_b200.so`` (C ABI declared in ``include/torchpme_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or a call fails the
+error is raised to the caller.  PyTorch is used for device memory and streams only; every
+function here takes torch tensors, checks that they are contiguous CUDA tensors and hands
+raw device pointers to the library on torch's current stream.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_LIB_NAME = "libtorchpme_b200.so"
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+P3M, LAGRANGE = 0, 1
+METHOD_ID = {"P3M": P3M, "Lagrange": LAGRANGE}
+GREEN_TABLE, GREEN_COULOMB, GREEN_IPL = 0, 1, 2
+
+# number of kernel launches issued through this binding (bench.py reports it)
+launch_counter = 0
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class _Green(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int),
+        ("exponent", ctypes.c_int),
+        ("p3m_nodes", ctypes.c_int),
+        ("reserved", ctypes.c_int),
+        ("smearing", ctypes.c_double),
+        ("prefactor", ctypes.c_double),
+        ("scale", ctypes.c_double),
+        ("recip", ctypes.c_double * 9),
+        ("spacing", ctypes.c_double * 3),
+        ("table", ctypes.c_void_p),
+    ]
+
+
+class _PairPotential(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int),
+        ("exponent", ctypes.c_int),
+        ("exclusion_degree", ctypes.c_int),
+        ("reserved", ctypes.c_int),
+        ("smearing", ctypes.c_double),
+        ("prefactor", ctypes.c_double),
+        ("exclusion_radius", ctypes.c_double),
+    ]
+
+
+_vp, _i, _i64, _dp = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)
+
+#: every symbol the header declares, with its argument types (used by the loader and by
+#: tests/test_abi.py to check the export table)
+SIGNATURES = {
+    "tpme_abi_version": ([], _i),
+    "tpme_last_error": ([], ctypes.c_char_p),
+    "tpme_spread": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
+    "tpme_gather": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "tpme_gather_vjp": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp], _i),
+    "tpme_fft_plan_create": ([ctypes.POINTER(_vp), _i, _i, _i, _i, _i], _i),
+    "tpme_fft_plan_destroy": ([_vp], _i),
+    "tpme_rfft3": ([_vp, _vp, _vp, _vp], _i),
+    "tpme_irfft3": ([_vp, _vp, _vp, _vp], _i),
+    "tpme_green_multiply": ([_i, _vp, _i, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
+    "tpme_kfilter_apply": ([_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_Green), _vp], _i),
+    "tpme_green_table": ([_i, _vp, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
+    "tpme_green_table_vjp": ([_i, _vp, _vp, _i, _i, _i, _i, ctypes.c_double, _vp, _vp], _i),
+    "tpme_pair_forward": ([_i, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _i, _i,
+                           ctypes.POINTER(_PairPotential), _vp, _vp], _i),
+    "tpme_pair_backward": ([_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i,
+                            ctypes.POINTER(_PairPotential), _vp, _vp, _vp], _i),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises NativeLibraryError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise NativeLibraryError(
+                f"{_LIB_NAME} not found at {_LIB_PATH}. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                "`make -C torch-pme_b200/csrc`. There is no CPU / PyTorch fallback."
+            )
+        lib = ctypes.CDLL(_LIB_PATH, mode=ctypes.RTLD_LOCAL)
+        for name, (argtypes, restype) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        if lib.tpme_abi_version() != 1:
+            raise NativeLibraryError("ABI version mismatch between header and library")
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().tpme_last_error().decode(errors="replace")
+        raise NativeLibraryError(f"{what} failed (code {rc}): {msg}")
+
+
+def _dtype_id(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.float64:
+        return 1
+    raise TypeError(f"torchpme_b200 kernels support float32/float64, got {t.dtype}")
+
+
+def _dev(t: torch.Tensor | None, name: str):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeLibraryError(
+            f"`{name}` lives on {t.device}; torchpme_b200 is a CUDA-only implementation "
+            "(no CPU fallback). Move the inputs to a CUDA device."
+        )
+    if not t.is_contiguous():
+        raise NativeLibraryError(f"`{name}` must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _on(t: torch.Tensor, name: str):
+    """device guard for the launch; refuses non-CUDA tensors loudly (no CPU fallback)"""
+    if not t.is_cuda:
+        raise NativeLibraryError(
+            f"`{name}` lives on {t.device}; torchpme_b200 is a CUDA-only implementation "
+            "(no CPU fallback). Move the inputs to a CUDA device."
+        )
+    return torch.cuda.device(t.device)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _mat9(values) -> ctypes.Array:
+    return (ctypes.c_double * 9)(*[float(v) for v in values])
+
+
+def _count(n=1):
+    global launch_counter
+    launch_counter += n
+
+
+# --------------------------------------------------------------------------------------
+# mesh interpolation
+# --------------------------------------------------------------------------------------
+def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None):
+    lib = load()
+    n, c = weights.shape
+    nx, ny, nz = ns
+    if out is None:
+        out = torch.empty((c, nx, ny, nz), dtype=positions.dtype, device=positions.device)
+    with _on(positions, "positions"):
+        _check(lib.tpme_spread(_dtype_id(positions), _dev(positions, "positions"),
+                               _dev(weights, "particle_weights"), n, c, _mat9(r2u), nx, ny, nz,
+                               nodes, method, _dev(out, "mesh"), 0, _stream()), "tpme_spread")
+    _count(2)
+    return out
+
+
+def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want_grad=False):
+    lib = load()
+    c, nx, ny, nz = mesh.shape
+    n = positions.shape[0]
+    values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device) if want_values else None
+    dvalues = torch.empty((n, c, 3), dtype=mesh.dtype, device=mesh.device) if want_grad else None
+    with _on(mesh, "mesh"):
+        _check(lib.tpme_gather(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"), n,
+                               c, _mat9(r2u), nx, ny, nz, nodes, method, _dev(values, "values"),
+                               _dev(dvalues, "dvalues"), _stream()), "tpme_gather")
+    _count()
+    return values, dvalues
+
+
+def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positions=None,
+               want_values=False, want_grad_r2u=False):
+    """returns (grad_positions, values | None, grad_r2u (3,3) | None)"""
+    lib = load()
+    c, nx, ny, nz = mesh.shape
+    n = positions.shape[0]
+    accumulate = grad_positions is not None
+    if grad_positions is None:
+        grad_positions = torch.empty((n, 3), dtype=mesh.dtype, device=mesh.device)
+    values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device) if want_values else None
+    grad_r2u = torch.zeros((3, 3), dtype=mesh.dtype, device=mesh.device) if want_grad_r2u else None
+    with _on(mesh, "mesh"):
+        _check(lib.tpme_gather_vjp(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"),
+                                   _dev(coef, "coef"), n, c, _mat9(r2u), nx, ny, nz, nodes, method,
+                                   _dev(grad_positions, "grad_positions"), _dev(values, "values"),
+                                   int(accumulate), _dev(grad_r2u, "grad_r2u"), _stream()),
+               "tpme_gather_vjp")
+    _count()
+    return grad_positions, values, grad_r2u
+
+
+# --------------------------------------------------------------------------------------
+# reciprocal space
+# --------------------------------------------------------------------------------------
+class FFTPlan:
+    """cuFFT R2C/C2R plan pair for a (batch, nx, ny, nz) real mesh."""
+
+    def __init__(self, dtype: torch.dtype, ns, batch: int, device):
+        lib = load()
+        self.ns = tuple(int(v) for v in ns)
+        self.batch = int(batch)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(lib.tpme_fft_plan_create(ctypes.byref(handle), 0 if dtype == torch.float32 else 1,
+                                            *self.ns, self.batch), "tpme_fft_plan_create")
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.tpme_fft_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_plan_cache: dict = {}
+
+
+def get_plan(dtype, ns, batch, device) -> FFTPlan:
+    key = (dtype, tuple(int(v) for v in ns), int(batch), torch.device(device).index)
+    plan = _plan_cache.get(key)
+    if plan is None:
+        if len(_plan_cache) > 32:
+            _plan_cache.clear()
+        plan = _plan_cache[key] = FFTPlan(dtype, ns, batch, device)
+    return plan
+
+
+def make_green(kind, scale, recip, spacing=(0.0, 0.0, 0.0), smearing=1.0, prefactor=1.0,
+               exponent=1, p3m_nodes=0, table=None) -> _Green:
+    g = _Green()
+    g.kind, g.exponent, g.p3m_nodes = int(kind), int(exponent), int(p3m_nodes)
+    g.smearing, g.prefactor, g.scale = float(smearing), float(prefactor), float(scale)
+    for k in range(9):
+        g.recip[k] = float(recip[k])
+    for k in range(3):
+        g.spacing[k] = float(spacing[k])
+    g.table = table.data_ptr() if table is not None else None
+    g._keepalive = table
+    return g
+
+
+def half_complex_shape(mesh_shape):
+    c, nx, ny, nz = mesh_shape
+    return (c, nx, ny, nz // 2 + 1, 2)
+
+
+def kfilter_apply(mesh, green: _Green, keep_hat=False):
+    """irfft3(G * rfft3(mesh)); returns (filtered mesh, rfft3(mesh) or None)."""
+    lib = load()
+    c, nx, ny, nz = mesh.shape
+    plan = get_plan(mesh.dtype, (nx, ny, nz), c, mesh.device)
+    out = torch.empty_like(mesh)
+    work = torch.empty(half_complex_shape(mesh.shape), dtype=mesh.dtype, device=mesh.device)
+    kept = torch.empty_like(work) if keep_hat else None
+    with _on(mesh, "mesh"):
+        _check(lib.tpme_kfilter_apply(plan.handle, _dev(mesh, "mesh_values"), _dev(out, "out"),
+                                      _dev(work, "work"), _dev(kept, "keep"), ctypes.byref(green),
+                                      _stream()), "tpme_kfilter_apply")
+    _count(4 if keep_hat else 3)
+    return out, kept
+
+
+def rfft3(mesh):
+    lib = load()
+    c, nx, ny, nz = mesh.shape
+    plan = get_plan(mesh.dtype, (nx, ny, nz), c, mesh.device)
+    hat = torch.empty(half_complex_shape(mesh.shape), dtype=mesh.dtype, device=mesh.device)
+    with _on(mesh, "mesh"):
+        _check(lib.tpme_rfft3(plan.handle, _dev(mesh, "mesh"), _dev(hat, "hat"), _stream()), "tpme_rfft3")
+    _count()
+    return hat
+
+
+def green_table(dtype, ns, green: _Green, device):
+    lib = load()
+    nx, ny, nz = ns
+    out = torch.empty((nx, ny, nz // 2 + 1), dtype=dtype, device=device)
+    with torch.cuda.device(device):
+        _check(lib.tpme_green_table(0 if dtype == torch.float32 else 1, _dev(out, "table"), nx, ny, nz,
+                                    ctypes.byref(green), _stream()), "tpme_green_table")
+    _count()
+    return out
+
+
+def green_table_vjp(x_hat, y_hat, ns, scale: float):
+    lib = load()
+    nx, ny, nz = ns
+    c = x_hat.shape[0]
+    out = torch.empty((nx, ny, nz // 2 + 1), dtype=x_hat.dtype, device=x_hat.device)
+    with _on(x_hat, "x_hat"):
+        _check(lib.tpme_green_table_vjp(_dtype_id(x_hat), _dev(x_hat, "x_hat"), _dev(y_hat, "y_hat"), c,
+                                        nx, ny, nz, float(scale), _dev(out, "grad_table"), _stream()),
+               "tpme_green_table_vjp")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# real space
+# --------------------------------------------------------------------------------------
+def make_pair_potential(kind, smearing=1.0, prefactor=1.0, exponent=1, exclusion_radius=None,
+                        exclusion_degree=1) -> _PairPotential:
+    p = _PairPotential()
+    p.kind, p.exponent, p.exclusion_degree = int(kind), int(exponent), int(exclusion_degree)
+    p.smearing, p.prefactor = float(smearing), float(prefactor)
+    p.exclusion_radius = float(exclusion_radius) if exclusion_radius is not None else -1.0
+    return p
+
+
+def _index_args(idx):
+    if idx.dtype == torch.int64:
+        return 1
+    if idx.dtype == torch.int32:
+        return 0
+    raise TypeError(f"neighbor_indices must be int32 or int64, got {idx.dtype}")
+
+
+def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot: _PairPotential):
+    lib = load()
+    n, c = charges.shape
+    out = torch.zeros_like(charges)
+    with _on(charges, "charges"):
+        _check(lib.tpme_pair_forward(_dtype_id(charges), _dev(charges, "charges"),
+                                     _dev(idx, "neighbor_indices"), _index_args(idx),
+                                     _dev(dist, "neighbor_distances"), _dev(pair_values, "pair_values"),
+                                     _dev(mask_u8, "pair_mask"), idx.shape[0], n, c, int(full_list),
+                                     ctypes.byref(pot), _dev(out, "out"), _stream()), "tpme_pair_forward")
+    _count(2)
+    return out
+
+
+def pair_backward(charges, idx, dist, pair_values, mask_u8, grad_out, full_list: bool,
+                  pot: _PairPotential, want_charges=True, want_pairs=True):
+    lib = load()
+    n, c = charges.shape
+    g_q = torch.zeros_like(charges) if want_charges else None
+    g_p = torch.empty(idx.shape[0], dtype=charges.dtype, device=charges.device) if want_pairs else None
+    with _on(charges, "charges"):
+        _check(lib.tpme_pair_backward(_dtype_id(charges), _dev(charges, "charges"),
+                                      _dev(idx, "neighbor_indices"), _index_args(idx),
+                                      _dev(dist, "neighbor_distances"), _dev(pair_values, "pair_values"),
+                                      _dev(mask_u8, "pair_mask"), _dev(grad_out, "grad_out"),
+                                      idx.shape[0], n, c, int(full_list), ctypes.byref(pot),
+                                      _dev(g_q, "grad_charges"), _dev(g_p, "grad_pairs"), _stream()),
+               "tpme_pair_backward")
+    _count(2 if want_charges else 1)
+    return g_q, g_p

@@ -1,0 +1,10 @@
+"""``torchpme.lib``-compatible namespace for the mesh building blocks."""
+from ..mesh import (  # noqa: F401
+    KSpaceFilter,
+    KSpaceKernel,
+    MeshInterpolator,
+    P3MKSpaceFilter,
+    generate_kvectors_for_mesh,
+    get_ns_mesh,
+)
+from ..potentials import exp1, gamma, gammaincc_over_powerlaw  # noqa: F401

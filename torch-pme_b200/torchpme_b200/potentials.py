@@ -1,0 +1,276 @@
+"""
+Pair potentials understood by the B200 calculators.
+
+Host-side mirror of the reference potential interface
+(``src/torchpme/potentials/{potential,coulomb,inversepowerlaw}.py``): same class names,
+constructor arguments, method names and error texts, so user code that builds
+``CoulombPotential(smearing=...)`` and hands it to a calculator keeps working.
+
+The torch implementations of the methods below are *interface* code: they serve users
+who call a potential directly and the differentiable "table" route of the k-space filter
+(cell gradients, custom kernels).  On the calculators' fast path none of them runs -- the
+short-range kernel and the Green's function are evaluated inside the CUDA kernels from
+the scalar description returned by :meth:`Potential._native_descriptor`.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _native
+
+_SQRT2 = math.sqrt(2.0)
+
+
+class _Exp1(torch.autograd.Function):
+    """E1(x) with the series / continued-fraction split of ``lib/math.py:16-60``."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        out = torch.full_like(x, torch.inf)
+        lo = (x > 0) & (x <= 1)
+        hi = x > 1
+        if bool(lo.any()):
+            xs = x[lo]
+            term = torch.ones_like(xs)
+            total = torch.ones_like(xs)
+            for k in range(1, 26):
+                term = -term * k * xs / (k + 1.0) ** 2
+                total = total + term
+                if bool(torch.all(term.abs() <= total.abs() * 1e-15)):
+                    break
+            out[lo] = -0.5772156649015329 - torch.log(xs) + xs * total
+        if bool(hi.any()):
+            xl = x[hi]
+            depth = int((20 + (80.0 / xl).to(torch.int32)).max())
+            levels = 20 + (80.0 / xl).to(torch.int32)
+            frac = torch.zeros_like(xl)
+            for k in range(depth, 0, -1):
+                # elements whose own depth is smaller than k start later (frac stays 0)
+                nxt = k / (1.0 + k / (xl + frac))
+                frac = torch.where(levels >= k, nxt, frac)
+            out[hi] = torch.exp(-xl) / (xl + frac)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (x,) = ctx.saved_tensors
+        return -grad * torch.exp(-x) / x
+
+
+def exp1(x: torch.Tensor) -> torch.Tensor:
+    """Exponential integral E1 for x > 0."""
+    return _Exp1.apply(x)
+
+
+def gamma(x: torch.Tensor) -> torch.Tensor:
+    """Complete gamma function through ``lgamma`` (``lib/math.py:5-13``)."""
+    return torch.exp(torch.special.gammaln(x))
+
+
+def gammaincc_over_powerlaw(exponent, z: torch.Tensor) -> torch.Tensor:
+    """Gamma((3-p)/2, z) / z^((3-p)/2) for p = 1..6 (``lib/math.py:79-104``)."""
+    p = int(exponent)
+    if p == 1:
+        return torch.exp(-z) / z
+    if p == 2:
+        return torch.sqrt(torch.pi / z) * torch.erfc(torch.sqrt(z))
+    if p == 3:
+        return exp1(z)
+    if p == 4:
+        return 2 * (torch.exp(-z) - torch.sqrt(torch.pi * z) * torch.erfc(torch.sqrt(z)))
+    if p == 5:
+        return torch.exp(-z) - z * exp1(z)
+    if p == 6:
+        root = torch.sqrt(torch.pi * z**3)
+        return ((2 - 4 * z) * torch.exp(-z) + 4 * root * torch.erfc(torch.sqrt(z))) / 3
+    raise ValueError(f"Unsupported exponent: {exponent}")
+
+
+def _slab_correction(periodic, positions, cell, charges):
+    """2-D periodic (slab) term of the 1/r potential (``potentials/coulomb.py:6-40``)."""
+    if periodic is None:
+        return torch.zeros_like(charges)
+    flags = periodic.to(torch.bool)
+    is_slab = flags.sum() == 2
+    axis = torch.argmax((~flags).to(torch.int64) * is_slab.to(torch.int64))
+    z = positions.index_select(1, axis.reshape(1))
+    length = torch.linalg.norm(cell, dim=-1).index_select(0, axis.reshape(1))
+    volume = torch.abs(torch.linalg.det(cell))
+    q_tot = charges.sum(dim=0)
+    m1 = (charges * z).sum(dim=0)
+    m2 = (charges * z * z).sum(dim=0)
+    slab = (4.0 * torch.pi / volume) * (z * m1 - 0.5 * (m2 + q_tot * z * z) - q_tot / 12.0 * length**2)
+    return torch.where(is_slab, slab, torch.zeros_like(slab))
+
+
+class Potential(torch.nn.Module):
+    """
+    Base class: range-separated pair potential V = V_SR + V_LR with smearing ``smearing``,
+    optional inner exclusion zone and a global ``prefactor``
+    (reference: ``potentials/potential.py:4-212``).
+    """
+
+    def __init__(self, smearing=None, exclusion_radius=None, exclusion_degree: int = 1,
+                 prefactor: float = 1.0):
+        super().__init__()
+        if smearing is None:
+            self.smearing = None
+        else:
+            self.register_buffer("smearing", torch.tensor(smearing, dtype=torch.float64))
+        self.exclusion_radius = exclusion_radius
+        self.exclusion_degree = exclusion_degree
+        self.register_buffer("prefactor", torch.tensor(prefactor, dtype=torch.float64))
+        self._host_scalars = None
+
+    # -- scalar description for the CUDA kernels ------------------------------------------
+    def _scalars(self):
+        """(smearing, prefactor) as Python floats, cached (reading a CUDA buffer syncs once)."""
+        key = (None if self.smearing is None else (self.smearing.data_ptr(), self.smearing._version),
+               self.prefactor.data_ptr(), self.prefactor._version)
+        if self._host_scalars is None or self._host_scalars[0] != key:
+            s = None if self.smearing is None else float(self.smearing)
+            self._host_scalars = (key, s, float(self.prefactor))
+        return self._host_scalars[1], self._host_scalars[2]
+
+    def _native_descriptor(self):
+        """``None`` (generic torch route) or ``(green_kind, exponent)`` for in-kernel evaluation."""
+        return None
+
+    # -- interface -------------------------------------------------------------------------
+    def f_cutoff(self, dist, pair_mask=None):
+        if self.exclusion_radius is None:
+            raise ValueError("Cannot compute cutoff function when `exclusion_radius` is not set")
+        bump = (0.5 * (1 - torch.cos(torch.pi * (dist / self.exclusion_radius)))) ** self.exclusion_degree
+        out = torch.where(dist < self.exclusion_radius, 1 - bump, 0.0)
+        return out if pair_mask is None else out * pair_mask
+
+    def from_dist(self, dist, pair_mask=None):
+        raise NotImplementedError(f"from_dist is not implemented for {self.__class__.__name__}")
+
+    def lr_from_dist(self, dist, pair_mask=None):
+        raise NotImplementedError(f"lr_from_dist is not implemented for {self.__class__.__name__}")
+
+    def lr_from_k_sq(self, k_sq):
+        raise NotImplementedError(f"lr_from_k_sq is not implemented for {self.__class__.__name__}")
+
+    def sr_from_dist(self, dist, pair_mask=None):
+        if self.smearing is None:
+            raise ValueError(
+                "Cannot compute range-separated potential when `smearing` is not specified."
+            )
+        long_range = self.lr_from_dist(dist, pair_mask=pair_mask)
+        if self.exclusion_radius is None:
+            return self.from_dist(dist, pair_mask=pair_mask) - long_range
+        return -long_range * self.f_cutoff(dist, pair_mask=pair_mask)
+
+    def kernel_from_k_sq(self, k_sq):
+        return self.lr_from_k_sq(k_sq)
+
+    def self_contribution(self):
+        raise NotImplementedError(f"self_contribution is not implemented for {self.__class__.__name__}")
+
+    def background_correction(self):
+        raise NotImplementedError(
+            f"background_correction is not implemented for {self.__class__.__name__}"
+        )
+
+    def pbc_correction(self, periodic, positions, cell, charges):
+        return self.prefactor * torch.zeros_like(charges)
+
+    def _need_smearing(self, what: str):
+        if self.smearing is None:
+            raise ValueError(f"Cannot compute {what} without specifying `smearing`.")
+
+
+def _masked(values, pair_mask):
+    return values if pair_mask is None else values * pair_mask
+
+
+class CoulombPotential(Potential):
+    """Smoothed 1/r potential (reference: ``potentials/coulomb.py:43-171``)."""
+
+    def _native_descriptor(self):
+        return (_native.GREEN_COULOMB, 1) if type(self) is CoulombPotential else None
+
+    def from_dist(self, dist, pair_mask=None):
+        return self.prefactor * _masked(1.0 / dist.clamp(min=1e-15), pair_mask)
+
+    def lr_from_dist(self, dist, pair_mask=None):
+        self._need_smearing("long-range contribution")
+        val = torch.erf(dist / self.smearing / _SQRT2) / dist.clamp(min=1e-12)
+        return self.prefactor * _masked(val, pair_mask)
+
+    def lr_from_k_sq(self, k_sq):
+        self._need_smearing("long-range kernel")
+        at_zero = k_sq == 0
+        safe = torch.where(at_zero, 1.0, k_sq)  # keeps the backward NaN free
+        val = 4 * torch.pi * torch.exp(-0.5 * self.smearing**2 * safe) / safe
+        return self.prefactor * torch.where(at_zero, 0.0, val)
+
+    def self_contribution(self):
+        self._need_smearing("self contribution")
+        return self.prefactor * math.sqrt(2 / math.pi) / self.smearing
+
+    def background_correction(self):
+        self._need_smearing("background correction")
+        return self.prefactor * torch.pi * self.smearing**2
+
+    def pbc_correction(self, periodic, positions, cell, charges):
+        return self.prefactor * _slab_correction(periodic, positions, cell, charges)
+
+
+class InversePowerLawPotential(Potential):
+    """1/r^p potentials, p = 1..6 (reference: ``potentials/inversepowerlaw.py:10-173``)."""
+
+    def __init__(self, exponent: int, smearing=None, exclusion_radius=None,
+                 exclusion_degree: int = 1, prefactor: float = 1.0):
+        super().__init__(smearing, exclusion_radius, exclusion_degree, prefactor)
+        gammaincc_over_powerlaw(exponent, torch.tensor(1.0))  # validates the exponent
+        self.register_buffer("exponent", torch.tensor(exponent, dtype=torch.float64))
+        self._p = int(exponent)
+
+    def _native_descriptor(self):
+        return (_native.GREEN_IPL, self._p) if type(self) is InversePowerLawPotential else None
+
+    def from_dist(self, dist, pair_mask=None):
+        return self.prefactor * _masked(torch.pow(dist.clamp(min=1e-15), -self.exponent), pair_mask)
+
+    def lr_from_dist(self, dist, pair_mask=None):
+        self._need_smearing("long-range contribution")
+        half_p = self.exponent / 2
+        x = (0.5 * dist**2 / self.smearing**2).clamp(min=1e-15)
+        scale = 1.0 / (2 * self.smearing**2) ** half_p
+        val = scale * torch.special.gammainc(half_p, x) / x**half_p
+        return self.prefactor * _masked(val, pair_mask)
+
+    def lr_from_k_sq(self, k_sq):
+        self._need_smearing("long-range kernel")
+        p_eff = (3 - self.exponent) / 2
+        scale = torch.pi**1.5 / gamma(self.exponent / 2) * (2 * self.smearing**2) ** p_eff
+        z = 0.5 * self.smearing**2 * k_sq
+        safe = torch.where(z == 0, 1.0, z)
+        # k = 0: divergent for p <= 3 (dropped: neutralising background), finite for p > 3
+        at_zero = -scale / p_eff if self._p > 3 else 0.0
+        body = scale * gammaincc_over_powerlaw(self._p, safe)
+        return self.prefactor * torch.where(k_sq == 0, at_zero, body)
+
+    def self_contribution(self):
+        self._need_smearing("self contribution")
+        half_p = self.exponent / 2
+        return self.prefactor / gamma(half_p + 1) / (2 * self.smearing**2) ** half_p
+
+    def background_correction(self):
+        self._need_smearing("background correction")
+        if self._p >= 3:
+            return torch.zeros_like(self.smearing)
+        num = torch.pi**1.5 * (2 * self.smearing**2) ** ((3 - self.exponent) / 2)
+        return self.prefactor * num / ((3 - self.exponent) * gamma(self.exponent / 2))
+
+    def pbc_correction(self, periodic, positions, cell, charges):
+        if self._p == 1:
+            return self.prefactor * _slab_correction(periodic, positions, cell, charges)
+        return super().pbc_correction(periodic, positions, cell, charges)
