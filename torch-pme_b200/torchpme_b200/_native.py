@@ -178,7 +178,7 @@ def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None):
         _check(lib.tpme_spread(_dtype_id(positions), _dev(positions, "positions"),
                                _dev(weights, "particle_weights"), n, c, _mat9(r2u), nx, ny, nz,
                                nodes, method, _dev(out, "mesh"), 0, _stream()), "tpme_spread")
-    _count(2)
+    _count()
     return out
 
 
@@ -287,7 +287,7 @@ def kfilter_apply(mesh, green: _Green, keep_hat=False):
         _check(lib.tpme_kfilter_apply(plan.handle, _dev(mesh, "mesh_values"), _dev(out, "out"),
                                       _dev(work, "work"), _dev(kept, "keep"), ctypes.byref(green),
                                       _stream()), "tpme_kfilter_apply")
-    _count(4 if keep_hat else 3)
+    _count()  # Green multiply (the cuFFT kernels are library launches)
     return out, kept
 
 
@@ -298,7 +298,6 @@ def rfft3(mesh):
     hat = torch.empty(half_complex_shape(mesh.shape), dtype=mesh.dtype, device=mesh.device)
     with _on(mesh, "mesh"):
         _check(lib.tpme_rfft3(plan.handle, _dev(mesh, "mesh"), _dev(hat, "hat"), _stream()), "tpme_rfft3")
-    _count()
     return hat
 
 
@@ -356,7 +355,7 @@ def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot:
                                      _dev(dist, "neighbor_distances"), _dev(pair_values, "pair_values"),
                                      _dev(mask_u8, "pair_mask"), idx.shape[0], n, c, int(full_list),
                                      ctypes.byref(pot), _dev(out, "out"), _stream()), "tpme_pair_forward")
-    _count(2)
+    _count()
     return out
 
 
@@ -374,5 +373,5 @@ def pair_backward(charges, idx, dist, pair_values, mask_u8, grad_out, full_list:
                                       idx.shape[0], n, c, int(full_list), ctypes.byref(pot),
                                       _dev(g_q, "grad_charges"), _dev(g_p, "grad_pairs"), _stream()),
                "tpme_pair_backward")
-    _count(2 if want_charges else 1)
+    _count()
     return g_q, g_p
