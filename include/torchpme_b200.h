@@ -40,13 +40,29 @@ int tpme_spread(int dtype, const void* positions, const void* weights, int64_t n
                 int n_channels, const double* r2u_host, int nx, int ny, int nz, int nodes,
                 int method, void* mesh, int accumulate, void* stream);
 
+/* Optional fused O(N) epilogue of the gathers (NULL = plain gather).  With it
+ *   values[i,c]  = values[i,c] + scale * gathered - add_coef[i,c] * self_half - background * dc[c]
+ * which folds the 1/(2 V) factor, the self term and the neutralising-background term of
+ * calculators/pme.py:117-143 into the gather (dc[c] = sum_i q[i,c], see tpme_kfilter_apply), and
+ *   grad_positions[i,:] = vjp_scale * (vjp + sum_c coef2[i,c] * dvalues2[i,c,:])   (if coef2 != NULL)
+ * which adds the saved forward derivative to the backward gather. */
+typedef struct tpme_point_epilogue {
+  const void* add_coef;   /* (N,C) device */
+  const void* dc;         /* (C,) device */
+  double scale, self_half, background;
+  const void* coef2;      /* (N,C) device, may be NULL */
+  const void* dvalues2;   /* (N,C,3) device */
+  double vjp_scale;
+} tpme_point_epilogue;
+
 /* replaces MeshInterpolator.mesh_to_points (mesh_interpolator.py:428-457).
  *   values[i, c]      = sum_m mesh[c, m] * wx wy wz              (may be NULL)
  *   dvalues[i, c, :]  = d values[i, c] / d positions[i, :]        (may be NULL)
  * i.e. what PyTorch's tape yields by differentiating the weight polynomials. */
 int tpme_gather(int dtype, const void* mesh, const void* positions, int64_t n_points,
                 int n_channels, const double* r2u_host, int nx, int ny, int nz, int nodes,
-                int method, void* values, void* dvalues, void* stream);
+                int method, void* values, void* dvalues, const tpme_point_epilogue* epilogue,
+                void* stream);
 
 /* vector-Jacobian product shared by the backward of spread and gather:
  *   grad_positions[i, :] (+)= sum_c coef[i, c] * d/dr_i sum_m mesh[c, m] wx wy wz
@@ -56,7 +72,8 @@ int tpme_gather(int dtype, const void* mesh, const void* positions, int64_t n_po
 int tpme_gather_vjp(int dtype, const void* mesh, const void* positions, const void* coef,
                     int64_t n_points, int n_channels, const double* r2u_host, int nx, int ny,
                     int nz, int nodes, int method, void* grad_positions, void* values,
-                    int accumulate, void* grad_r2u, void* stream);
+                    int accumulate, void* grad_r2u, const tpme_point_epilogue* epilogue,
+                    void* stream);
 
 /* ---- reciprocal space ---------------------------------------------------------------
  * replaces KSpaceFilter.update + forward and P3MKSpaceFilter
@@ -88,13 +105,15 @@ typedef struct tpme_green {
   const void* table;   /* device, kind == 0 */
 } tpme_green;
 
-/* mesh_hat[c, k] *= scale * G(k) (in place) */
+/* mesh_hat[c, k] *= scale * G(k) (in place).  If `dc_out` (device, C reals) is non-NULL it
+ * receives Re mesh_hat[c, k=0] before the multiply, i.e. the sum of the real-space mesh. */
 int tpme_green_multiply(int dtype, void* mesh_hat, int n_channels, int nx, int ny, int nz,
-                        const tpme_green* green_host, void* stream);
+                        const tpme_green* green_host, void* dc_out, void* stream);
 /* out = irfft3(G * rfft3(in)); `work_hat` is caller-provided scratch of the half-complex
- * shape; if `keep_hat` is non-NULL the un-multiplied spectrum rfft3(in) is copied there. */
+ * shape; if `keep_hat` is non-NULL the un-multiplied spectrum rfft3(in) is copied there;
+ * `dc_out` as above. */
 int tpme_kfilter_apply(tpme_fft_plan plan, const void* mesh_in, void* mesh_out, void* work_hat,
-                       void* keep_hat, const tpme_green* green_host, void* stream);
+                       void* keep_hat, const tpme_green* green_host, void* dc_out, void* stream);
 /* writes the filter itself, (nx,ny,nz/2+1) reals: scale * G(k) */
 int tpme_green_table(int dtype, void* table_out, int nx, int ny, int nz,
                      const tpme_green* green_host, void* stream);

@@ -47,7 +47,7 @@ def test_argument_errors_are_reported_without_a_gpu():
 
     lib = _native.load()
     green = _native.make_green(2, 1.0, [0.0] * 9, exponent=9)
-    rc = lib.tpme_green_multiply(0, None, 1, 4, 4, 4, ctypes.byref(green), None)
+    rc = lib.tpme_green_multiply(0, None, 1, 4, 4, 4, ctypes.byref(green), None, None)
     assert rc != 0
     assert b"Unsupported exponent" in lib.tpme_last_error()
     rc = lib.tpme_spread(7, None, None, 1, 1, (ctypes.c_double * 9)(), 4, 4, 4, 4, 0, None, 0, None)

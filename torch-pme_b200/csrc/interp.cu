@@ -84,12 +84,28 @@ template <int N> struct GroupSize {
   static constexpr int value = (N * N <= 1) ? 1 : (N * N <= 4) ? 4 : (N * N <= 16) ? 16 : 32;
 };
 
+// Optional fused epilogues (all pointers may be null):
+//   values[i,c] = values[i,c] + scale * val - add_coef[i,c] * self_half - background * dc[c]
+//     (the O(N) self / background corrections and the 1/(2V) factor of calculators/pme.py:117-143)
+//   grad_positions[i,:] = vjp_scale * (vjp + sum_c coef2[i,c] * dvalues2[i,c,:])
+template <typename T>
+struct PointEpilogue {
+  const T* add_coef;
+  const T* dc;
+  T scale, self_half, background;
+  const T* coef2;
+  const T* dvalues2;
+  T vjp_scale;
+  int enabled;
+};
+
 template <typename T, int METHOD, int N, int MODE>
 __global__ void __launch_bounds__(256)
 gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
               const T* __restrict__ coef, int64_t n_points, int n_channels, Mat3<T> r2u, int nx,
               int ny, int nz, T* __restrict__ values, T* __restrict__ dvalues,
-              T* __restrict__ grad_positions, int accumulate, T* __restrict__ grad_r2u) {
+              T* __restrict__ grad_positions, int accumulate, T* __restrict__ grad_r2u,
+              PointEpilogue<T> epi) {
   constexpr int G = GroupSize<N>::value;
   constexpr bool DERIV = (MODE & 6) != 0;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,7 +156,14 @@ gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
       }
     }
     if (lane == 0 && valid) {
-      if (MODE & 1) values[point * n_channels + ch] = val;
+      if (MODE & 1) {
+        const int64_t o = point * n_channels + ch;
+        if (epi.enabled)
+          values[o] = values[o] + epi.scale * val - epi.add_coef[o] * epi.self_half -
+                      epi.background * epi.dc[ch];
+        else
+          values[o] = val;
+      }
       if (MODE & 2) {
         T* out = dvalues + (point * n_channels + ch) * 3;
 #pragma unroll
@@ -160,7 +183,12 @@ gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
       T* out = grad_positions + 3 * point;
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
-        const T g = r2u.m[3 * b] * gu[0] + r2u.m[3 * b + 1] * gu[1] + r2u.m[3 * b + 2] * gu[2];
+        T g = r2u.m[3 * b] * gu[0] + r2u.m[3 * b + 1] * gu[1] + r2u.m[3 * b + 2] * gu[2];
+        if (epi.enabled && epi.coef2 != nullptr) {
+          for (int ch = 0; ch < n_channels; ++ch)
+            g = fma_t(epi.coef2[point * n_channels + ch], epi.dvalues2[(point * n_channels + ch) * 3 + b], g);
+          g *= epi.vjp_scale;
+        }
         out[b] = accumulate ? out[b] + g : g;
       }
     }
@@ -207,8 +235,20 @@ template <typename T, int METHOD, int N, int MODE>
 int launch_gather(const void* mesh, const void* positions, const void* coef, int64_t n_points,
                   int n_channels, const double* r2u, int nx, int ny, int nz, void* values,
                   void* dvalues, void* grad_positions, int accumulate, void* grad_r2u,
-                  cudaStream_t stream) {
+                  const tpme_point_epilogue* epi_host, cudaStream_t stream) {
   constexpr int G = GroupSize<N>::value;
+  PointEpilogue<T> epi;
+  epi.enabled = epi_host != nullptr;
+  if (epi_host) {
+    epi.add_coef = (const T*)epi_host->add_coef; epi.dc = (const T*)epi_host->dc;
+    epi.scale = (T)epi_host->scale; epi.self_half = (T)epi_host->self_half;
+    epi.background = (T)epi_host->background;
+    epi.coef2 = (const T*)epi_host->coef2; epi.dvalues2 = (const T*)epi_host->dvalues2;
+    epi.vjp_scale = (T)epi_host->vjp_scale;
+  } else {
+    epi.add_coef = epi.dc = epi.coef2 = epi.dvalues2 = nullptr;
+    epi.scale = epi.self_half = epi.background = epi.vjp_scale = T(0);
+  }
   const int64_t threads = n_points * G;
   const int block = 256;
   const int64_t grid = (threads + block - 1) / block;
@@ -216,7 +256,7 @@ int launch_gather(const void* mesh, const void* positions, const void* coef, int
   gather_kernel<T, METHOD, N, MODE><<<(unsigned)grid, block, 0, stream>>>(
       (const T*)mesh, (const T*)positions, (const T*)coef, n_points, n_channels,
       load_mat3<T>(r2u), nx, ny, nz, (T*)values, (T*)dvalues, (T*)grad_positions, accumulate,
-      (T*)grad_r2u);
+      (T*)grad_r2u, epi);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -256,10 +296,10 @@ template <typename T, int MODE>
 int gather_dispatch(const void* mesh, const void* positions, const void* coef, int64_t n_points,
                     int n_channels, const double* r2u, int nx, int ny, int nz, int nodes,
                     int method, void* values, void* dvalues, void* grad_positions, int accumulate,
-                    void* grad_r2u, cudaStream_t stream) {
+                    void* grad_r2u, const tpme_point_epilogue* epi, cudaStream_t stream) {
 #define CALL(M, N)                                                                              \
   launch_gather<T, M, N, MODE>(mesh, positions, coef, n_points, n_channels, r2u, nx, ny, nz,   \
-                               values, dvalues, grad_positions, accumulate, grad_r2u, stream)
+                               values, dvalues, grad_positions, accumulate, grad_r2u, epi, stream)
   TPME_DISPATCH_STENCIL(CALL)
 #undef CALL
 }
@@ -294,7 +334,8 @@ extern "C" int tpme_spread(int dtype, const void* positions, const void* weights
 
 extern "C" int tpme_gather(int dtype, const void* mesh, const void* positions, int64_t n_points,
                            int n_channels, const double* r2u_host, int nx, int ny, int nz,
-                           int nodes, int method, void* values, void* dvalues, void* stream) {
+                           int nodes, int method, void* values, void* dvalues,
+                           const tpme_point_epilogue* epilogue, void* stream) {
   if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
   TPME_REQUIRE(values != nullptr || dvalues != nullptr, "nothing to compute");
   if (n_points == 0 || n_channels == 0) return 0;
@@ -303,7 +344,7 @@ extern "C" int tpme_gather(int dtype, const void* mesh, const void* positions, i
 #define GO(T, MODE)                                                                          \
   return gather_dispatch<T, MODE>(mesh, positions, nullptr, n_points, n_channels, r2u_host,  \
                                   nx, ny, nz, nodes, method, values, dvalues, nullptr, 0,    \
-                                  nullptr, s)
+                                  nullptr, epilogue, s)
   if (dtype == 0) {
     if (mode == 1) GO(float, 1);
     if (mode == 2) GO(float, 2);
@@ -319,7 +360,8 @@ extern "C" int tpme_gather_vjp(int dtype, const void* mesh, const void* position
                                const void* coef, int64_t n_points, int n_channels,
                                const double* r2u_host, int nx, int ny, int nz, int nodes,
                                int method, void* grad_positions, void* values, int accumulate,
-                               void* grad_r2u, void* stream) {
+                               void* grad_r2u, const tpme_point_epilogue* epilogue,
+                               void* stream) {
   if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
   TPME_REQUIRE(grad_positions != nullptr && coef != nullptr, "grad_positions / coef missing");
   if (n_points == 0) return 0;
@@ -332,7 +374,7 @@ extern "C" int tpme_gather_vjp(int dtype, const void* mesh, const void* position
 #define GO(T, MODE)                                                                           \
   return gather_dispatch<T, MODE>(mesh, positions, coef, n_points, n_channels, r2u_host, nx,  \
                                   ny, nz, nodes, method, values, nullptr, grad_positions,     \
-                                  accumulate, grad_r2u, s)
+                                  accumulate, grad_r2u, epilogue, s)
   if (dtype == 0) {
     if (values) GO(float, 5);
     GO(float, 4);

@@ -121,7 +121,8 @@ __device__ __forceinline__ T green_value(const GreenDev<T>& g, int ix, int iy, i
 // S = storage type of the mesh, T = arithmetic type of the Green's function
 template <typename S, typename T>
 __global__ void __launch_bounds__(256)
-green_multiply_kernel(S* __restrict__ hat, int n_channels, int nx, int ny, int nz, GreenDev<T> g) {
+green_multiply_kernel(S* __restrict__ hat, int n_channels, int nx, int ny, int nz, GreenDev<T> g,
+                      S* __restrict__ dc_out) {
   const int nzh = nz / 2 + 1;
   const int64_t total = (int64_t)nx * ny * nzh;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -133,6 +134,7 @@ green_multiply_kernel(S* __restrict__ hat, int n_channels, int nx, int ny, int n
     const S gv = (S)green_value<T, S>(g, ix, iy, iz, nx, ny, nz, i);
     for (int c = 0; c < n_channels; ++c) {
       S* p = hat + 2 * (c * total + i);
+      if (i == 0 && dc_out != nullptr) dc_out[c] = p[0];
       if (sizeof(S) == 4) {
         float2 v = *reinterpret_cast<float2*>(p);
         v.x *= gv; v.y *= gv;
@@ -307,7 +309,7 @@ extern "C" int tpme_irfft3(tpme_fft_plan plan, void* mesh_hat, void* mesh, void*
 }
 
 extern "C" int tpme_green_multiply(int dtype, void* mesh_hat, int n_channels, int nx, int ny,
-                                   int nz, const tpme_green* green, void* stream) {
+                                   int nz, const tpme_green* green, void* dc_out, void* stream) {
   if (int rc = check_green(green)) return rc;
   TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 or 1");
   const int64_t total = (int64_t)nx * ny * (nz / 2 + 1);
@@ -315,11 +317,11 @@ extern "C" int tpme_green_multiply(int dtype, void* mesh_hat, int n_channels, in
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = green_grid(total);
   if (dtype == 1)
-    green_multiply_kernel<double, double><<<grid, 256, 0, s>>>((double*)mesh_hat, n_channels, nx, ny, nz, make_green<double>(green));
+    green_multiply_kernel<double, double><<<grid, 256, 0, s>>>((double*)mesh_hat, n_channels, nx, ny, nz, make_green<double>(green), (double*)dc_out);
   else if (needs_double_math(green))
-    green_multiply_kernel<float, double><<<grid, 256, 0, s>>>((float*)mesh_hat, n_channels, nx, ny, nz, make_green<double>(green));
+    green_multiply_kernel<float, double><<<grid, 256, 0, s>>>((float*)mesh_hat, n_channels, nx, ny, nz, make_green<double>(green), (float*)dc_out);
   else
-    green_multiply_kernel<float, float><<<grid, 256, 0, s>>>((float*)mesh_hat, n_channels, nx, ny, nz, make_green<float>(green));
+    green_multiply_kernel<float, float><<<grid, 256, 0, s>>>((float*)mesh_hat, n_channels, nx, ny, nz, make_green<float>(green), (float*)dc_out);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -360,13 +362,13 @@ extern "C" int tpme_green_table_vjp(int dtype, const void* x_hat, const void* y_
 
 extern "C" int tpme_kfilter_apply(tpme_fft_plan plan, const void* mesh_in, void* mesh_out,
                                   void* work_hat, void* keep_hat, const tpme_green* green,
-                                  void* stream) {
+                                  void* dc_out, void* stream) {
   TPME_REQUIRE(plan != nullptr, "null plan");
   if (int rc = tpme_rfft3(plan, mesh_in, work_hat, stream)) return rc;
   if (keep_hat != nullptr) {
     const size_t bytes = (size_t)(plan->dtype ? 16 : 8) * plan->batch * plan->nx * plan->ny * (plan->nz / 2 + 1);
     TPME_CUDA_OK(cudaMemcpyAsync(keep_hat, work_hat, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   }
-  if (int rc = tpme_green_multiply(plan->dtype, work_hat, plan->batch, plan->nx, plan->ny, plan->nz, green, stream)) return rc;
+  if (int rc = tpme_green_multiply(plan->dtype, work_hat, plan->batch, plan->nx, plan->ny, plan->nz, green, dc_out, stream)) return rc;
   return tpme_irfft3(plan, work_hat, mesh_out, stream);
 }

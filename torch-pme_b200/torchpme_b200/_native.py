@@ -57,6 +57,19 @@ class _PairPotential(ctypes.Structure):
     ]
 
 
+class _PointEpilogue(ctypes.Structure):
+    _fields_ = [
+        ("add_coef", ctypes.c_void_p),
+        ("dc", ctypes.c_void_p),
+        ("scale", ctypes.c_double),
+        ("self_half", ctypes.c_double),
+        ("background", ctypes.c_double),
+        ("coef2", ctypes.c_void_p),
+        ("dvalues2", ctypes.c_void_p),
+        ("vjp_scale", ctypes.c_double),
+    ]
+
+
 _vp, _i, _i64, _dp = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)
 
 #: every symbol the header declares, with its argument types (used by the loader and by
@@ -65,14 +78,16 @@ SIGNATURES = {
     "tpme_abi_version": ([], _i),
     "tpme_last_error": ([], ctypes.c_char_p),
     "tpme_spread": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
-    "tpme_gather": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
-    "tpme_gather_vjp": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp], _i),
+    "tpme_gather": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp,
+                     ctypes.POINTER(_PointEpilogue), _vp], _i),
+    "tpme_gather_vjp": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp,
+                         ctypes.POINTER(_PointEpilogue), _vp], _i),
     "tpme_fft_plan_create": ([ctypes.POINTER(_vp), _i, _i, _i, _i, _i], _i),
     "tpme_fft_plan_destroy": ([_vp], _i),
     "tpme_rfft3": ([_vp, _vp, _vp, _vp], _i),
     "tpme_irfft3": ([_vp, _vp, _vp, _vp], _i),
-    "tpme_green_multiply": ([_i, _vp, _i, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
-    "tpme_kfilter_apply": ([_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_Green), _vp], _i),
+    "tpme_green_multiply": ([_i, _vp, _i, _i, _i, _i, ctypes.POINTER(_Green), _vp, _vp], _i),
+    "tpme_kfilter_apply": ([_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_Green), _vp, _vp], _i),
     "tpme_green_table": ([_i, _vp, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
     "tpme_green_table_vjp": ([_i, _vp, _vp, _i, _i, _i, _i, ctypes.c_double, _vp, _vp], _i),
     "tpme_pair_forward": ([_i, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _i, _i,
@@ -182,22 +197,41 @@ def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None):
     return out
 
 
-def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want_grad=False):
+def make_epilogue(add_coef, dc, scale, self_half, background, coef2=None, dvalues2=None,
+                  vjp_scale=0.0) -> _PointEpilogue:
+    e = _PointEpilogue()
+    e.add_coef, e.dc = add_coef.data_ptr(), dc.data_ptr()
+    e.scale, e.self_half, e.background = float(scale), float(self_half), float(background)
+    e.coef2 = coef2.data_ptr() if coef2 is not None else None
+    e.dvalues2 = dvalues2.data_ptr() if dvalues2 is not None else None
+    e.vjp_scale = float(vjp_scale)
+    e._keepalive = (add_coef, dc, coef2, dvalues2)
+    return e
+
+
+def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want_grad=False,
+           values_out=None, epilogue: _PointEpilogue | None = None):
+    """plain gather, or (with `epilogue` and `values_out`) the fused accumulate form"""
     lib = load()
     c, nx, ny, nz = mesh.shape
     n = positions.shape[0]
-    values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device) if want_values else None
+    values = values_out
+    if values is None and want_values:
+        values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device)
     dvalues = torch.empty((n, c, 3), dtype=mesh.dtype, device=mesh.device) if want_grad else None
     with _on(mesh, "mesh"):
         _check(lib.tpme_gather(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"), n,
                                c, _mat9(r2u), nx, ny, nz, nodes, method, _dev(values, "values"),
-                               _dev(dvalues, "dvalues"), _stream()), "tpme_gather")
+                               _dev(dvalues, "dvalues"),
+                               ctypes.byref(epilogue) if epilogue is not None else None, _stream()),
+               "tpme_gather")
     _count()
     return values, dvalues
 
 
 def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positions=None,
-               want_values=False, want_grad_r2u=False):
+               want_values=False, want_grad_r2u=False, values_out=None,
+               epilogue: _PointEpilogue | None = None):
     """returns (grad_positions, values | None, grad_r2u (3,3) | None)"""
     lib = load()
     c, nx, ny, nz = mesh.shape
@@ -205,14 +239,17 @@ def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positio
     accumulate = grad_positions is not None
     if grad_positions is None:
         grad_positions = torch.empty((n, 3), dtype=mesh.dtype, device=mesh.device)
-    values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device) if want_values else None
+    values = values_out
+    if values is None and want_values:
+        values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device)
     grad_r2u = torch.zeros((3, 3), dtype=mesh.dtype, device=mesh.device) if want_grad_r2u else None
     with _on(mesh, "mesh"):
         _check(lib.tpme_gather_vjp(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"),
                                    _dev(coef, "coef"), n, c, _mat9(r2u), nx, ny, nz, nodes, method,
                                    _dev(grad_positions, "grad_positions"), _dev(values, "values"),
-                                   int(accumulate), _dev(grad_r2u, "grad_r2u"), _stream()),
-               "tpme_gather_vjp")
+                                   int(accumulate), _dev(grad_r2u, "grad_r2u"),
+                                   ctypes.byref(epilogue) if epilogue is not None else None,
+                                   _stream()), "tpme_gather_vjp")
     _count()
     return grad_positions, values, grad_r2u
 
@@ -275,19 +312,22 @@ def half_complex_shape(mesh_shape):
     return (c, nx, ny, nz // 2 + 1, 2)
 
 
-def kfilter_apply(mesh, green: _Green, keep_hat=False):
-    """irfft3(G * rfft3(mesh)); returns (filtered mesh, rfft3(mesh) or None)."""
+def kfilter_apply(mesh, green: _Green, keep_hat=False, want_dc=False):
+    """irfft3(G * rfft3(mesh)); returns (filtered mesh, rfft3(mesh) | None[, sum of the mesh (C,)])."""
     lib = load()
     c, nx, ny, nz = mesh.shape
     plan = get_plan(mesh.dtype, (nx, ny, nz), c, mesh.device)
     out = torch.empty_like(mesh)
     work = torch.empty(half_complex_shape(mesh.shape), dtype=mesh.dtype, device=mesh.device)
     kept = torch.empty_like(work) if keep_hat else None
+    dc = torch.empty(c, dtype=mesh.dtype, device=mesh.device) if want_dc else None
     with _on(mesh, "mesh"):
         _check(lib.tpme_kfilter_apply(plan.handle, _dev(mesh, "mesh_values"), _dev(out, "out"),
                                       _dev(work, "work"), _dev(kept, "keep"), ctypes.byref(green),
-                                      _stream()), "tpme_kfilter_apply")
+                                      _dev(dc, "dc"), _stream()), "tpme_kfilter_apply")
     _count()  # Green multiply (the cuFFT kernels are library launches)
+    if want_dc:
+        return out, kept, dc
     return out, kept
 
 
@@ -345,10 +385,13 @@ def _index_args(idx):
     raise TypeError(f"neighbor_indices must be int32 or int64, got {idx.dtype}")
 
 
-def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot: _PairPotential):
+def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot: _PairPotential,
+                 out=None):
+    """accumulates into `out` (allocated and zeroed here when None)"""
     lib = load()
     n, c = charges.shape
-    out = torch.zeros_like(charges)
+    if out is None:
+        out = torch.zeros_like(charges)
     with _on(charges, "charges"):
         _check(lib.tpme_pair_forward(_dtype_id(charges), _dev(charges, "charges"),
                                      _dev(idx, "neighbor_indices"), _index_args(idx),
@@ -360,10 +403,12 @@ def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot:
 
 
 def pair_backward(charges, idx, dist, pair_values, mask_u8, grad_out, full_list: bool,
-                  pot: _PairPotential, want_charges=True, want_pairs=True):
+                  pot: _PairPotential, want_charges=True, want_pairs=True, grad_charges_out=None):
     lib = load()
     n, c = charges.shape
-    g_q = torch.zeros_like(charges) if want_charges else None
+    g_q = grad_charges_out
+    if g_q is None and want_charges:
+        g_q = torch.zeros_like(charges)
     g_p = torch.empty(idx.shape[0], dtype=charges.dtype, device=charges.device) if want_pairs else None
     with _on(charges, "charges"):
         _check(lib.tpme_pair_backward(_dtype_id(charges), _dev(charges, "charges"),

@@ -45,6 +45,71 @@ class _PairSum(torch.autograd.Function):
         return g_q, g_x, None, None, None, None
 
 
+class _FusedStepConfig:
+    """by-value launch parameters of one fused PME / P3M evaluation"""
+    __slots__ = ("r2u", "ns", "nodes", "method", "green_args", "pair_pot", "full_list",
+                 "half_ivolume", "self_half", "background_ivolume")
+
+
+class _FusedMeshPotential(torch.autograd.Function):
+    """
+    Whole calculator forward as one autograd node (fast path: in-kernel potential, no cell
+    gradient, 3-D periodic):
+
+        V = pair_sum(q, d) + 1/(2 Vol) gather(A spread(q)) - q self/2 - bg sum(q)/Vol
+
+    Six kernel launches forward (pair, spread, FFT . G . iFFT, gather with the O(N) corrections
+    fused as epilogue, which also emits dV/dr) and five backward (pair backward, spread of the
+    incoming gradient, FFT . G . iFFT, gather + derivative gather with the saved dV/dr folded in).
+    """
+
+    @staticmethod
+    def forward(ctx, charges, positions, distances, neighbor_indices, mask_u8, cfg):
+        q = charges.detach().contiguous()
+        pos = positions.detach().contiguous()
+        d = distances.detach().contiguous()
+        idx = neighbor_indices.contiguous()
+        need_pos = ctx.needs_input_grad[1]
+        out = torch.zeros_like(q)
+        _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
+        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+        green = _native.make_green(scale=1.0, **cfg.green_args)
+        phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
+        epi = _native.make_epilogue(q, dc, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume)
+        _, dvalues = _native.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=need_pos,
+                                    values_out=out, epilogue=epi)
+        ctx.cfg = cfg
+        ctx.save_for_backward(q, pos, d, idx, mask_u8, dvalues)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        q, pos, d, idx, mask_u8, dvalues = ctx.saved_tensors
+        cfg = ctx.cfg
+        need_q, need_pos, need_d = ctx.needs_input_grad[:3]
+        g = grad_out.contiguous()
+        g_q = torch.zeros_like(q) if need_q else None
+        g_d = None
+        if need_q or need_d:
+            _, g_d = _native.pair_backward(q, idx, d, None, mask_u8, g, cfg.full_list, cfg.pair_pot,
+                                           want_charges=need_q, want_pairs=need_d, grad_charges_out=g_q)
+        g_pos = None
+        if need_q or need_pos:
+            rho_g = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+            green = _native.make_green(scale=1.0, **cfg.green_args)
+            psi, _, dc_g = _native.kfilter_apply(rho_g, green, want_dc=True)
+            epi = _native.make_epilogue(g, dc_g, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume,
+                                        coef2=g if need_pos else None, dvalues2=dvalues,
+                                        vjp_scale=cfg.half_ivolume)
+            if need_pos:
+                g_pos, _, _ = _native.gather_vjp(psi, pos, q, cfg.r2u, cfg.nodes, cfg.method,
+                                                 values_out=g_q, epilogue=epi)
+            else:
+                _native.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi)
+        return g_q, g_pos, g_d, None, None, None
+
+
 class Calculator(torch.nn.Module):
     """
     Real-space part V_i = 1/2 sum_j q_j v(r_ij) over a neighbor list, plus the long-range
@@ -112,6 +177,7 @@ class PMECalculator(Calculator):
             raise ValueError(f"`smearing` is {potential.smearing} but must be positive")
         self.mesh_spacing = mesh_spacing
         self.interpolation_nodes = interpolation_nodes
+        self._fused_cfg = self._fused_key = self._fused_geom = None
         unit = torch.eye(3, device=potential.smearing.device, dtype=potential.smearing.dtype)
         ones = torch.ones(3, dtype=torch.int64, device=unit.device)
         self.kspace_filter = self._make_filter(unit, ones)
@@ -119,6 +185,48 @@ class PMECalculator(Calculator):
 
     def _make_filter(self, cell, ns):
         return KSpaceFilter(cell, ns, kernel=self.potential, fft_norm="backward", ifft_norm="forward")
+
+    def _fast_path_ok(self, cell, periodic, node_mask, kvectors) -> bool:
+        pot = self.potential
+        if periodic is not None or node_mask is not None or kvectors is not None:
+            return False
+        if pot._native_descriptor() is None or cell.requires_grad:
+            return False
+        return not any(t.requires_grad for t in list(pot.parameters()) + list(pot.buffers()))
+
+    def forward(self, charges, cell, positions, neighbor_indices, neighbor_distances,
+                periodic=None, node_mask=None, pair_mask=None, kvectors=None):
+        if not self._fast_path_ok(cell, periodic, node_mask, kvectors):
+            return super().forward(charges, cell, positions, neighbor_indices, neighbor_distances,
+                                   periodic, node_mask, pair_mask, kvectors)
+        validate_parameters(charges, cell, positions, neighbor_indices, neighbor_distances,
+                            periodic, pair_mask, node_mask, kvectors)
+        pot = self.potential
+        geom = geometry_of(cell)
+        ns = geom.ns_mesh(self.mesh_spacing)
+        kind, exponent = pot._native_descriptor()
+        smearing, prefactor = pot._scalars()
+        key = (id(geom), ns, kind, exponent, smearing, prefactor, pot.exclusion_radius,
+               pot.exclusion_degree, self.full_neighbor_list)
+        cfg = self._fused_cfg if self._fused_key == key else None
+        if cfg is None:
+            cfg = _FusedStepConfig()
+            cfg.r2u, cfg.ns = geom.r2u(ns), ns
+            cfg.nodes, cfg.method = self.interpolation_nodes, _native.METHOD_ID[self._method]
+            cfg.green_args = dict(kind=kind, exponent=exponent, smearing=smearing, prefactor=prefactor,
+                                  recip=geom.recip, spacing=geom.spacing(ns),
+                                  p3m_nodes=self.interpolation_nodes if self._method == "P3M" else 0)
+            cfg.pair_pot = _native.make_pair_potential(kind, smearing, prefactor, exponent,
+                                                       pot.exclusion_radius, pot.exclusion_degree)
+            cfg.full_list = self.full_neighbor_list
+            ivolume = 1.0 / geom.volume
+            cfg.half_ivolume = 0.5 * ivolume
+            cfg.self_half = 0.5 * float(pot.self_contribution())
+            cfg.background_ivolume = float(pot.background_correction()) * ivolume
+            self._fused_cfg, self._fused_key, self._fused_geom = cfg, key, geom
+        mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
+        return _FusedMeshPotential.apply(charges, positions, neighbor_distances, neighbor_indices,
+                                         mask_u8, cfg)
 
     def _compute_kspace(self, charges, cell, positions, periodic=None, node_mask=None, kvectors=None):
         if node_mask is not None or kvectors is not None:
