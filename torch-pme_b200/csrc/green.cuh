@@ -1,0 +1,166 @@
+// Green's / influence functions evaluated per k-point from the reciprocal cell (shared by the
+// stand-alone multiply kernel and the fused x-pass of the hand-written FFT).
+//
+// Reference: generate_kvectors_for_mesh (lib/kvectors.py:24-102), Potential.lr_from_k_sq
+// (potentials/coulomb.py:122-142, potentials/inversepowerlaw.py:108-141, lib/math.py:16-104),
+// P3MKSpaceFilter._compute_influence (lib/kspace_filter.py:307-316,349-361).
+#pragma once
+#include <cmath>
+
+#include "common.cuh"
+#include "../../include/torchpme_b200.h"
+
+namespace tpme {
+
+// ---- special functions ---------------------------------------------------------------
+template <typename T> struct MathFn;
+template <> struct MathFn<float> {
+  static __device__ __forceinline__ float exp(float x) { return expf(x); }
+  static __device__ __forceinline__ float log(float x) { return logf(x); }
+  static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float erfc(float x) { return erfcf(x); }
+  static __device__ __forceinline__ float sin(float x) { return sinf(x); }
+  static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+  static __device__ __forceinline__ void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+};
+template <> struct MathFn<double> {
+  static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+  static __device__ __forceinline__ double log(double x) { return ::log(x); }
+  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ double erfc(double x) { return ::erfc(x); }
+  static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
+  static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+  static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+};
+
+// Exponential integral E1, same algorithm as lib/math.py:16-60 (series for x <= 1,
+// continued fraction with 20 + floor(80/x) levels above).
+template <typename T>
+__device__ T exp1_dev(T x) {
+  using M = MathFn<T>;
+  if (!(x > T(0))) return T(INFINITY);
+  if (x <= T(1)) {
+    T e1 = T(1), r = T(1);
+    for (int k = 1; k < 26; ++k) {
+      const T kp = T(k + 1);
+      r = -r * T(k) * x / (kp * kp);
+      e1 += r;
+      if (M::abs(r) <= M::abs(e1) * T(1e-15)) break;
+    }
+    return T(-0.577215664901532860606512090082402431) - M::log(x) + x * e1;
+  }
+  const int m = 20 + (int)(T(80) / x);
+  T t0 = T(0);
+  for (int k = m; k > 0; --k) t0 = T(k) / (T(1) + T(k) / (x + t0));
+  return M::exp(-x) / (x + t0);
+}
+
+// f_p(z) = Gamma((3-p)/2, z) / z^((3-p)/2)   (lib/math.py:79-104)
+template <typename T>
+__device__ T gammaincc_over_powerlaw_dev(int p, T z) {
+  using M = MathFn<T>;
+  const T pi = T(3.14159265358979323846);
+  switch (p) {
+    case 1: return M::exp(-z) / z;
+    case 2: return M::sqrt(pi / z) * M::erfc(M::sqrt(z));
+    case 3: return exp1_dev<T>(z);
+    case 4: return T(2) * (M::exp(-z) - M::sqrt(pi * z) * M::erfc(M::sqrt(z)));
+    case 5: return M::exp(-z) - z * exp1_dev<T>(z);
+    default:
+      return ((T(2) - T(4) * z) * M::exp(-z) + T(4) * M::sqrt(pi * z * z * z) * M::erfc(M::sqrt(z))) / T(3);
+  }
+}
+
+template <typename T>
+struct GreenDev {
+  int kind, exponent, p3m_nodes;
+  T recip[9];
+  T spacing[3];
+  T half_s2;      // smearing^2 / 2
+  T amplitude;    // scale * prefactor * (4 pi | ipl prefactor)
+  T k0_value;     // value at k = 0 (already scaled)
+  const void* table;
+};
+
+// scale * G(k) at integer mesh frequency (ix, iy, iz) of the rFFT layout
+template <typename T, typename S>
+__device__ __forceinline__ T green_value(const GreenDev<T>& g, int ix, int iy, int iz, int nx,
+                                         int ny, int nz, int64_t flat) {
+  using M = MathFn<T>;
+  if (g.kind == 0) return (T) reinterpret_cast<const S*>(g.table)[flat] * g.amplitude;
+  // fftfreq(n) * n  (lib/kvectors.py:56-70)
+  const T fx = (T)(ix < (nx + 1) / 2 ? ix : ix - nx);
+  const T fy = (T)(iy < (ny + 1) / 2 ? iy : iy - ny);
+  const T fz = (T)iz;
+  const T kx = fx * g.recip[0] + fy * g.recip[3] + fz * g.recip[6];
+  const T ky = fx * g.recip[1] + fy * g.recip[4] + fz * g.recip[7];
+  const T kz = fx * g.recip[2] + fy * g.recip[5] + fz * g.recip[8];
+  const T k_sq = kx * kx + ky * ky + kz * kz;
+  T val;
+  if (k_sq == T(0)) {
+    val = g.k0_value;
+  } else if (g.kind == 1 || g.exponent == 1) {
+    // 4 pi exp(-s^2 k^2 / 2) / k^2   (coulomb.py:137-142); IPL p=1 is identical
+    val = g.amplitude * M::exp(-g.half_s2 * k_sq) / (g.kind == 1 ? k_sq : g.half_s2 * k_sq);
+  } else {
+    val = g.amplitude * gammaincc_over_powerlaw_dev<T>(g.exponent, g.half_s2 * k_sq);
+  }
+  if (g.p3m_nodes > 0) {
+    // 1 / U^2, U^2 = [prod_a sinc(k_a h_a / 2 pi)]^(2n)   (kspace_filter.py:307-316,349-361)
+    const T hx = T(0.5) * kx * g.spacing[0], hy = T(0.5) * ky * g.spacing[1],
+            hz = T(0.5) * kz * g.spacing[2];
+    const T sx = hx == T(0) ? T(1) : M::sin(hx) / hx;
+    const T sy = hy == T(0) ? T(1) : M::sin(hy) / hy;
+    const T sz = hz == T(0) ? T(1) : M::sin(hz) / hz;
+    const T s = sx * sy * sz;
+    T u2 = T(1);
+    const T s2 = s * s;
+    for (int i = 0; i < g.p3m_nodes; ++i) u2 *= s2;
+    val = (u2 == T(0)) ? T(0) : val / u2;
+  }
+  return val;
+}
+
+template <typename T>
+inline GreenDev<T> make_green(const tpme_green* h) {
+  GreenDev<T> g;
+  g.kind = h->kind;
+  g.exponent = h->exponent;
+  g.p3m_nodes = h->p3m_nodes;
+  for (int i = 0; i < 9; ++i) g.recip[i] = (T)h->recip[i];
+  for (int i = 0; i < 3; ++i) g.spacing[i] = (T)h->spacing[i];
+  const double s2 = h->smearing * h->smearing;
+  g.half_s2 = (T)(0.5 * s2);
+  g.table = h->table;
+  const double pi = 3.14159265358979323846;
+  double amp = h->scale, k0 = 0.0;
+  if (h->kind == 1) {
+    amp *= h->prefactor * 4.0 * pi;
+  } else if (h->kind == 2) {
+    // prefac = pi^1.5 / Gamma(p/2) (2 s^2)^((3-p)/2)   (inversepowerlaw.py:121-125)
+    const double p = h->exponent;
+    const double peff = (3.0 - p) / 2.0;
+    const double pre = pow(pi, 1.5) / tgamma(p / 2.0) * pow(2.0 * s2, peff);
+    amp *= h->prefactor * pre;
+    if (h->exponent > 3) k0 = h->scale * h->prefactor * (-pre / peff);  // :134-137
+  }
+  g.amplitude = (T)amp;
+  g.k0_value = (T)k0;
+  return g;
+}
+
+inline int check_green(const tpme_green* g) {
+  TPME_REQUIRE(g != nullptr, "green parameters missing");
+  TPME_REQUIRE(g->kind >= 0 && g->kind <= 2, "green kind must be 0 (table), 1 (coulomb) or 2 (ipl)");
+  TPME_REQUIRE(g->kind != 0 || g->table != nullptr, "table kind needs a table pointer");
+  TPME_REQUIRE(g->kind != 2 || (g->exponent >= 1 && g->exponent <= 6), "Unsupported exponent");
+  TPME_REQUIRE(g->p3m_nodes >= 0 && g->p3m_nodes <= 7, "bad p3m_nodes");
+  return 0;
+}
+
+// IPL with p >= 2 has cancellations (erfc / E1 differences) -> evaluate G in double even
+// for float meshes; everything else uses the storage precision like the reference.
+inline bool needs_double_math(const tpme_green* g) { return g->kind == 2 && g->exponent >= 2; }
+
+
+}  // namespace tpme

@@ -6,117 +6,20 @@
 // (potentials/coulomb.py:122-142, potentials/inversepowerlaw.py:108-141, lib/math.py:16-104).
 #include <cufft.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
+#include "green.cuh"
 #include "../../include/torchpme_b200.h"
 
 namespace tpme {
 
-// ---- special functions ---------------------------------------------------------------
-template <typename T> struct MathFn;
-template <> struct MathFn<float> {
-  static __device__ __forceinline__ float exp(float x) { return expf(x); }
-  static __device__ __forceinline__ float log(float x) { return logf(x); }
-  static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
-  static __device__ __forceinline__ float erfc(float x) { return erfcf(x); }
-  static __device__ __forceinline__ float sin(float x) { return sinf(x); }
-  static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
-};
-template <> struct MathFn<double> {
-  static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
-  static __device__ __forceinline__ double log(double x) { return ::log(x); }
-  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-  static __device__ __forceinline__ double erfc(double x) { return ::erfc(x); }
-  static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
-  static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
-};
-
-// Exponential integral E1, same algorithm as lib/math.py:16-60 (series for x <= 1,
-// continued fraction with 20 + floor(80/x) levels above).
-template <typename T>
-__device__ T exp1_dev(T x) {
-  using M = MathFn<T>;
-  if (!(x > T(0))) return T(INFINITY);
-  if (x <= T(1)) {
-    T e1 = T(1), r = T(1);
-    for (int k = 1; k < 26; ++k) {
-      const T kp = T(k + 1);
-      r = -r * T(k) * x / (kp * kp);
-      e1 += r;
-      if (M::abs(r) <= M::abs(e1) * T(1e-15)) break;
-    }
-    return T(-0.577215664901532860606512090082402431) - M::log(x) + x * e1;
-  }
-  const int m = 20 + (int)(T(80) / x);
-  T t0 = T(0);
-  for (int k = m; k > 0; --k) t0 = T(k) / (T(1) + T(k) / (x + t0));
-  return M::exp(-x) / (x + t0);
-}
-
-// f_p(z) = Gamma((3-p)/2, z) / z^((3-p)/2)   (lib/math.py:79-104)
-template <typename T>
-__device__ T gammaincc_over_powerlaw_dev(int p, T z) {
-  using M = MathFn<T>;
-  const T pi = T(3.14159265358979323846);
-  switch (p) {
-    case 1: return M::exp(-z) / z;
-    case 2: return M::sqrt(pi / z) * M::erfc(M::sqrt(z));
-    case 3: return exp1_dev<T>(z);
-    case 4: return T(2) * (M::exp(-z) - M::sqrt(pi * z) * M::erfc(M::sqrt(z)));
-    case 5: return M::exp(-z) - z * exp1_dev<T>(z);
-    default:
-      return ((T(2) - T(4) * z) * M::exp(-z) + T(4) * M::sqrt(pi * z * z * z) * M::erfc(M::sqrt(z))) / T(3);
-  }
-}
-
-template <typename T>
-struct GreenDev {
-  int kind, exponent, p3m_nodes;
-  T recip[9];
-  T spacing[3];
-  T half_s2;      // smearing^2 / 2
-  T amplitude;    // scale * prefactor * (4 pi | ipl prefactor)
-  T k0_value;     // value at k = 0 (already scaled)
-  const void* table;
-};
-
-// scale * G(k) at integer mesh frequency (ix, iy, iz) of the rFFT layout
-template <typename T, typename S>
-__device__ __forceinline__ T green_value(const GreenDev<T>& g, int ix, int iy, int iz, int nx,
-                                         int ny, int nz, int64_t flat) {
-  using M = MathFn<T>;
-  if (g.kind == 0) return (T) reinterpret_cast<const S*>(g.table)[flat] * g.amplitude;
-  // fftfreq(n) * n  (lib/kvectors.py:56-70)
-  const T fx = (T)(ix < (nx + 1) / 2 ? ix : ix - nx);
-  const T fy = (T)(iy < (ny + 1) / 2 ? iy : iy - ny);
-  const T fz = (T)iz;
-  const T kx = fx * g.recip[0] + fy * g.recip[3] + fz * g.recip[6];
-  const T ky = fx * g.recip[1] + fy * g.recip[4] + fz * g.recip[7];
-  const T kz = fx * g.recip[2] + fy * g.recip[5] + fz * g.recip[8];
-  const T k_sq = kx * kx + ky * ky + kz * kz;
-  T val;
-  if (k_sq == T(0)) {
-    val = g.k0_value;
-  } else if (g.kind == 1 || g.exponent == 1) {
-    // 4 pi exp(-s^2 k^2 / 2) / k^2   (coulomb.py:137-142); IPL p=1 is identical
-    val = g.amplitude * M::exp(-g.half_s2 * k_sq) / (g.kind == 1 ? k_sq : g.half_s2 * k_sq);
-  } else {
-    val = g.amplitude * gammaincc_over_powerlaw_dev<T>(g.exponent, g.half_s2 * k_sq);
-  }
-  if (g.p3m_nodes > 0) {
-    // 1 / U^2, U^2 = [prod_a sinc(k_a h_a / 2 pi)]^(2n)   (kspace_filter.py:307-316,349-361)
-    const T hx = T(0.5) * kx * g.spacing[0], hy = T(0.5) * ky * g.spacing[1],
-            hz = T(0.5) * kz * g.spacing[2];
-    const T sx = hx == T(0) ? T(1) : M::sin(hx) / hx;
-    const T sy = hy == T(0) ? T(1) : M::sin(hy) / hy;
-    const T sz = hz == T(0) ? T(1) : M::sin(hz) / hz;
-    const T s = sx * sy * sz;
-    T u2 = T(1);
-    const T s2 = s * s;
-    for (int i = 0; i < g.p3m_nodes; ++i) u2 *= s2;
-    val = (u2 == T(0)) ? T(0) : val / u2;
-  }
-  return val;
-}
+// hand-written FFT . G . iFFT for power-of-two meshes (fft3d.cuh, instantiated in fft_*.cu)
+int filter_pow2_f32(const void*, void*, void*, int, int, int, int, const GreenDev<float>&, void*, cudaStream_t);
+int filter_pow2_f64(const void*, void*, void*, int, int, int, int, const GreenDev<double>&, void*, cudaStream_t);
+int filter_pow2_f32d(const void*, void*, void*, int, int, int, int, const GreenDev<double>&, void*, cudaStream_t);
+static bool fft_supported_dim(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
 
 // S = storage type of the mesh, T = arithmetic type of the Green's function
 template <typename S, typename T>
@@ -181,52 +84,11 @@ table_vjp_kernel(const S* __restrict__ x_hat, const S* __restrict__ y_hat, int n
   }
 }
 
-template <typename T>
-static GreenDev<T> make_green(const tpme_green* h) {
-  GreenDev<T> g;
-  g.kind = h->kind;
-  g.exponent = h->exponent;
-  g.p3m_nodes = h->p3m_nodes;
-  for (int i = 0; i < 9; ++i) g.recip[i] = (T)h->recip[i];
-  for (int i = 0; i < 3; ++i) g.spacing[i] = (T)h->spacing[i];
-  const double s2 = h->smearing * h->smearing;
-  g.half_s2 = (T)(0.5 * s2);
-  g.table = h->table;
-  const double pi = 3.14159265358979323846;
-  double amp = h->scale, k0 = 0.0;
-  if (h->kind == 1) {
-    amp *= h->prefactor * 4.0 * pi;
-  } else if (h->kind == 2) {
-    // prefac = pi^1.5 / Gamma(p/2) (2 s^2)^((3-p)/2)   (inversepowerlaw.py:121-125)
-    const double p = h->exponent;
-    const double peff = (3.0 - p) / 2.0;
-    const double pre = pow(pi, 1.5) / tgamma(p / 2.0) * pow(2.0 * s2, peff);
-    amp *= h->prefactor * pre;
-    if (h->exponent > 3) k0 = h->scale * h->prefactor * (-pre / peff);  // :134-137
-  }
-  g.amplitude = (T)amp;
-  g.k0_value = (T)k0;
-  return g;
-}
-
 static int green_grid(int64_t total) {
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 8;
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
-
-static int check_green(const tpme_green* g) {
-  TPME_REQUIRE(g != nullptr, "green parameters missing");
-  TPME_REQUIRE(g->kind >= 0 && g->kind <= 2, "green kind must be 0 (table), 1 (coulomb) or 2 (ipl)");
-  TPME_REQUIRE(g->kind != 0 || g->table != nullptr, "table kind needs a table pointer");
-  TPME_REQUIRE(g->kind != 2 || (g->exponent >= 1 && g->exponent <= 6), "Unsupported exponent");
-  TPME_REQUIRE(g->p3m_nodes >= 0 && g->p3m_nodes <= 7, "bad p3m_nodes");
-  return 0;
-}
-
-// IPL with p >= 2 has cancellations (erfc / E1 differences) -> evaluate G in double even
-// for float meshes; everything else uses the storage precision like the reference.
-static bool needs_double_math(const tpme_green* g) { return g->kind == 2 && g->exponent >= 2; }
 
 static const char* cufft_err(cufftResult r) {
   switch (r) {
@@ -255,6 +117,7 @@ static const char* cufft_err(cufftResult r) {
 struct tpme_fft_plan_s {
   cufftHandle fwd = 0, inv = 0;
   int dtype = 0, nx = 0, ny = 0, nz = 0, batch = 0;
+  bool own_fft = false;  // power-of-two mesh: hand-written fused FFT . G . iFFT (fft3d.cuh)
 };
 
 using namespace tpme;
@@ -276,9 +139,14 @@ extern "C" int tpme_fft_plan_create(tpme_fft_plan* plan, int dtype, int nx, int 
   cufftResult r2 = cufftPlanMany(&p->inv, 3, n, cembed, 1, cdist, rembed, 1, rdist,
                                  dtype == 0 ? CUFFT_C2R : CUFFT_Z2D, batch);
   if (r2 != CUFFT_SUCCESS) { cufftDestroy(p->fwd); delete p; set_last_error("cufftPlanMany(inv)", cufft_err(r2)); return 200 + (int)r2; }
+  const char* force = getenv("TPME_FFT");  // "cufft" forces the library path (A/B testing)
+  p->own_fft = fft_supported_dim(nx) && fft_supported_dim(ny) && fft_supported_dim(nz) &&
+               !(force != nullptr && strcmp(force, "cufft") == 0);
   *plan = p;
   return 0;
 }
+
+extern "C" int tpme_fft_plan_uses_own_fft(tpme_fft_plan plan) { return plan != nullptr && plan->own_fft; }
 
 extern "C" int tpme_fft_plan_destroy(tpme_fft_plan plan) {
   if (!plan) return 0;
@@ -364,6 +232,18 @@ extern "C" int tpme_kfilter_apply(tpme_fft_plan plan, const void* mesh_in, void*
                                   void* work_hat, void* keep_hat, const tpme_green* green,
                                   void* dc_out, void* stream) {
   TPME_REQUIRE(plan != nullptr, "null plan");
+  if (plan->own_fft && keep_hat == nullptr) {
+    if (int rc = check_green(green)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (plan->dtype == 1)
+      return filter_pow2_f64(mesh_in, mesh_out, work_hat, plan->batch, plan->nx, plan->ny, plan->nz,
+                             make_green<double>(green), dc_out, s);
+    if (needs_double_math(green))
+      return filter_pow2_f32d(mesh_in, mesh_out, work_hat, plan->batch, plan->nx, plan->ny, plan->nz,
+                              make_green<double>(green), dc_out, s);
+    return filter_pow2_f32(mesh_in, mesh_out, work_hat, plan->batch, plan->nx, plan->ny, plan->nz,
+                           make_green<float>(green), dc_out, s);
+  }
   if (int rc = tpme_rfft3(plan, mesh_in, work_hat, stream)) return rc;
   if (keep_hat != nullptr) {
     const size_t bytes = (size_t)(plan->dtype ? 16 : 8) * plan->batch * plan->nx * plan->ny * (plan->nz / 2 + 1);

@@ -84,6 +84,7 @@ SIGNATURES = {
                          ctypes.POINTER(_PointEpilogue), _vp], _i),
     "tpme_fft_plan_create": ([ctypes.POINTER(_vp), _i, _i, _i, _i, _i], _i),
     "tpme_fft_plan_destroy": ([_vp], _i),
+    "tpme_fft_plan_uses_own_fft": ([_vp], _i),
     "tpme_rfft3": ([_vp, _vp, _vp, _vp], _i),
     "tpme_irfft3": ([_vp, _vp, _vp, _vp], _i),
     "tpme_green_multiply": ([_i, _vp, _i, _i, _i, _i, ctypes.POINTER(_Green), _vp, _vp], _i),
