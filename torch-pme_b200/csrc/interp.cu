@@ -9,13 +9,36 @@
 
 namespace tpme {
 
-// Fractional mesh coordinate, stencil base index and 1-D weights of one point.
+// Fractional mesh coordinate, wrapped stencil origin and 1-D weights of one point.
 //   u = r @ r2u                                   (mesh_interpolator.py:326)
 //   even n: i0 = floor(u), x = u - (i0 + 1/2);  odd n: i0 = rint(u), x = u - i0   (:329-341)
-//   first node index = i0 + 1 - (n + 1) / 2                                        (:350-359)
+//   first node index = (i0 + 1 - (n + 1) / 2) mod ns                              (:350-359)
+// The modulo is done in floating point on the integer-valued base (exact), followed by a
+// compare-and-fix; no integer division.
+template <typename T>
+struct MeshDims {
+  int n[3];
+  T inv_n[3];
+};
+
+template <typename T>
+__device__ __forceinline__ int wrap_base(T base, int n, T inv_n) {
+  const T q = floor_t(base * inv_n);
+  int i = (int)(base - q * (T)n);
+  if (i < 0) i += n;
+  if (i >= n) i -= n;
+  return i;
+}
+
+__device__ __forceinline__ int wrap_add(int i, int n) {   // i in [0, 2n) typically; loop for n < nodes
+  while (i >= n) i -= n;
+  return i;
+}
+
 template <typename T, int METHOD, int N, bool DERIV>
 __device__ __forceinline__ void point_stencil(const T* __restrict__ pos, const Mat3<T>& r2u,
-                                              int (&first)[3], T (&w)[3][N], T (&dw)[3][N]) {
+                                              const MeshDims<T>& dims, int (&first)[3], T (&w)[3][N],
+                                              T (&dw)[3][N]) {
   const T r0 = pos[0], r1 = pos[1], r2 = pos[2];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -28,7 +51,7 @@ __device__ __forceinline__ void point_stencil(const T* __restrict__ pos, const M
       base = rint_t(u);
       x = u - base;
     }
-    first[a] = (int)base + 1 - (N + 1) / 2;
+    first[a] = wrap_base<T>(base + T(1 - (N + 1) / 2), dims.n[a], dims.inv_n[a]);
     Stencil<METHOD, N>::template eval<T, DERIV>(x, w[a], dw[a]);
   }
 }
@@ -41,49 +64,62 @@ __device__ __forceinline__ T pick(const T (&arr)[N], int k) {
   return out;
 }
 
+// A group of G = next_pow2(N) lanes serves one point; lane c owns the z offset c of the stencil
+// (the contiguous mesh axis, so a warp-wide access touches runs of N consecutive mesh values per
+// (x, y) row) and loops over the N x N (a, b) rows.  Only G lanes repeat the per-point weight
+// evaluation.
+template <int N> struct GroupSize {
+  static constexpr int value = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : 8;
+};
+
 // ---------------------------------------------------------------------------------------
-// spread: one thread per (point, a, b) stencil column; the z-run of N nodes is contiguous.
+// spread
 // ---------------------------------------------------------------------------------------
 template <typename T, int METHOD, int N>
 __global__ void __launch_bounds__(256)
 spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, int64_t n_points,
-              int n_channels, Mat3<T> r2u, int nx, int ny, int nz, T* __restrict__ mesh) {
+              int n_channels, Mat3<T> r2u, MeshDims<T> dims, T* __restrict__ mesh) {
+  constexpr int G = GroupSize<N>::value;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t point = tid / (N * N);
+  const int64_t point = tid / G;
   if (point >= n_points) return;
-  const int ab = (int)(tid - point * (N * N));
-  const int a = ab / N, b = ab - a * N;
+  const int c = (int)(tid - point * G);
+  if (c >= N) return;
 
   int first[3];
   T w[3][N], dw[3][N];
-  point_stencil<T, METHOD, N, false>(positions + 3 * point, r2u, first, w, dw);
-
-  const int ix = wrap_index(first[0] + a, nx);
-  const int iy = wrap_index(first[1] + b, ny);
-  const T wxy = pick<T, N>(w[0], a) * pick<T, N>(w[1], b);
-  const int64_t row = ((int64_t)ix * ny + iy) * nz;
-  const int64_t mesh_size = (int64_t)nx * ny * nz;
-  int iz = wrap_index(first[2], nz);
-  for (int ch = 0; ch < n_channels; ++ch) {
-    const T q = weights[point * n_channels + ch] * wxy;
-    T* dst = mesh + ch * mesh_size + row;
-    int z = iz;
+  point_stencil<T, METHOD, N, false>(positions + 3 * point, r2u, dims, first, w, dw);
+  const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
+  const unsigned plane = (unsigned)ny * nz;
+  const int64_t mesh_size = (int64_t)plane * nx;
+  unsigned xoff[N], yoff[N];
+  {
+    int ix = first[0], iy = first[1];
 #pragma unroll
-    for (int c = 0; c < N; ++c) {
-      red_add(dst + z, q * w[2][c]);
-      z = (z + 1 == nz) ? 0 : z + 1;
+    for (int a = 0; a < N; ++a) {
+      xoff[a] = (unsigned)ix * plane;
+      yoff[a] = (unsigned)iy * nz;
+      ix = (ix + 1 >= nx) ? wrap_add(ix + 1, nx) : ix + 1;
+      iy = (iy + 1 >= ny) ? wrap_add(iy + 1, ny) : iy + 1;
+    }
+  }
+  const unsigned iz = (unsigned)wrap_add(first[2] + c, nz);
+  const T wz = pick<T, N>(w[2], c);
+  for (int ch = 0; ch < n_channels; ++ch) {
+    const T q = weights[point * n_channels + ch] * wz;
+    T* dst = mesh + ch * mesh_size + iz;
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      const T qa = q * w[0][a];
+#pragma unroll
+      for (int b = 0; b < N; ++b) red_add(dst + (xoff[a] + yoff[b]), qa * w[1][b]);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// gather: a group of G lanes per point, lanes own (a, b) stencil columns, shuffle-reduce.
-//   MODE bit 0: values, bit 1: dvalues/dr, bit 2: vjp into grad_positions (+ grad_r2u)
+// gather.  MODE bit 0: values, bit 1: dvalues/dr, bit 2: vjp into grad_positions (+ grad_r2u)
 // ---------------------------------------------------------------------------------------
-template <int N> struct GroupSize {
-  static constexpr int value = (N * N <= 1) ? 1 : (N * N <= 4) ? 4 : (N * N <= 16) ? 16 : 32;
-};
-
 // Optional fused epilogues (all pointers may be null):
 //   values[i,c] = values[i,c] + scale * val - add_coef[i,c] * self_half - background * dc[c]
 //     (the O(N) self / background corrections and the 1/(2V) factor of calculators/pme.py:117-143)
@@ -99,11 +135,38 @@ struct PointEpilogue {
   int enabled;
 };
 
+// Sum four per-lane quantities over a group of G lanes (G = 1, 2, 4, 8): the first two steps
+// split the quantities between the halves, the rest is a butterfly; every lane gets the totals.
+template <typename T, int G>
+__device__ __forceinline__ void group_reduce4(T& q0, T& q1, T& q2, T& q3, int lane) {
+  if (G == 1) return;
+  if (G == 2) {
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 1, G);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, 1, G);
+    q2 += __shfl_xor_sync(0xffffffffu, q2, 1, G);
+    q3 += __shfl_xor_sync(0xffffffffu, q3, 1, G);
+    return;
+  }
+  const bool up = (lane & (G / 2)) != 0;
+  const T sa = up ? q0 : q2, sb = up ? q1 : q3;
+  T ka = (up ? q2 : q0) + __shfl_xor_sync(0xffffffffu, sa, G / 2, G);
+  T kb = (up ? q3 : q1) + __shfl_xor_sync(0xffffffffu, sb, G / 2, G);
+  const bool up2 = (lane & (G / 4)) != 0;
+  T r = (up2 ? kb : ka) + __shfl_xor_sync(0xffffffffu, up2 ? ka : kb, G / 4, G);
+#pragma unroll
+  for (int off = G / 8; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off, G);
+  // lane 0 of each quarter holds: quarter 0 -> q0, 1 -> q1, 2 -> q2, 3 -> q3
+  q0 = __shfl_sync(0xffffffffu, r, 0, G);
+  q1 = __shfl_sync(0xffffffffu, r, G / 4, G);
+  q2 = __shfl_sync(0xffffffffu, r, G / 2, G);
+  q3 = __shfl_sync(0xffffffffu, r, 3 * G / 4, G);
+}
+
 template <typename T, int METHOD, int N, int MODE>
 __global__ void __launch_bounds__(256)
 gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
-              const T* __restrict__ coef, int64_t n_points, int n_channels, Mat3<T> r2u, int nx,
-              int ny, int nz, T* __restrict__ values, T* __restrict__ dvalues,
+              const T* __restrict__ coef, int64_t n_points, int n_channels, Mat3<T> r2u,
+              MeshDims<T> dims, T* __restrict__ values, T* __restrict__ dvalues,
               T* __restrict__ grad_positions, int accumulate, T* __restrict__ grad_r2u,
               PointEpilogue<T> epi) {
   constexpr int G = GroupSize<N>::value;
@@ -113,47 +176,55 @@ gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
   const bool valid = point_raw < n_points;
   const int64_t point = valid ? point_raw : n_points - 1;
   const int lane = (int)(tid % G);
+  const bool active = lane < N;
 
   int first[3];
   T w[3][N], dw[3][N];
-  point_stencil<T, METHOD, N, DERIV>(positions + 3 * point, r2u, first, w, dw);
-  const int iz0 = wrap_index(first[2], nz);
-  const int64_t mesh_size = (int64_t)nx * ny * nz;
+  point_stencil<T, METHOD, N, DERIV>(positions + 3 * point, r2u, dims, first, w, dw);
+  const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
+  const unsigned plane = (unsigned)ny * nz;
+  const int64_t mesh_size = (int64_t)plane * nx;
+  unsigned xoff[N], yoff[N];
+  {
+    int ix = first[0], iy = first[1];
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+      xoff[a] = (unsigned)ix * plane;
+      yoff[a] = (unsigned)iy * nz;
+      ix = (ix + 1 >= nx) ? wrap_add(ix + 1, nx) : ix + 1;
+      iy = (iy + 1 >= ny) ? wrap_add(iy + 1, ny) : iy + 1;
+    }
+  }
+  const unsigned iz = (unsigned)wrap_add(first[2] + (active ? lane : 0), nz);
+  const T wz = active ? pick<T, N>(w[2], lane) : T(0);
+  const T dwz = (DERIV && active) ? pick<T, N>(dw[2], lane) : T(0);
 
   T gu[3] = {T(0), T(0), T(0)};  // vjp accumulator in mesh coordinates
   for (int ch = 0; ch < n_channels; ++ch) {
-    T val = T(0), du0 = T(0), du1 = T(0), du2 = T(0);
-    const T* src_ch = mesh + ch * mesh_size;
-    for (int ab = lane; ab < N * N; ab += G) {
-      const int a = ab / N, b = ab - a * N;
-      const int ix = wrap_index(first[0] + a, nx);
-      const int iy = wrap_index(first[1] + b, ny);
-      const T* src = src_ch + ((int64_t)ix * ny + iy) * nz;
-      T s = T(0), sd = T(0);
-      int z = iz0;
+    const T* src = mesh + ch * mesh_size + iz;
+    // S0 = sum_ab v wx wy, S1 = sum v dwx wy, S2 = sum v wx dwy   (this lane's z offset)
+    T s0 = T(0), s1 = T(0), s2 = T(0);
 #pragma unroll
-      for (int c = 0; c < N; ++c) {
-        const T v = __ldg(src + z);
-        s = fma_t(v, w[2][c], s);
-        if (DERIV) sd = fma_t(v, dw[2][c], sd);
-        z = (z + 1 == nz) ? 0 : z + 1;
+    for (int a = 0; a < N; ++a) {
+      T t0 = T(0), t1 = T(0);
+#pragma unroll
+      for (int b = 0; b < N; ++b) {
+        const T v = __ldg(src + (xoff[a] + yoff[b]));
+        t0 = fma_t(v, w[1][b], t0);
+        if (DERIV) t1 = fma_t(v, dw[1][b], t1);
       }
-      const T wa = pick<T, N>(w[0], a), wb = pick<T, N>(w[1], b);
-      val = fma_t(wa * wb, s, val);
+      s0 = fma_t(w[0][a], t0, s0);
       if (DERIV) {
-        du0 = fma_t(pick<T, N>(dw[0], a) * wb, s, du0);
-        du1 = fma_t(wa * pick<T, N>(dw[1], b), s, du1);
-        du2 = fma_t(wa * wb, sd, du2);
+        s1 = fma_t(dw[0][a], t0, s1);
+        s2 = fma_t(w[0][a], t1, s2);
       }
     }
+    T val = wz * s0, du0 = wz * s1, du1 = wz * s2, du2 = dwz * s0;
+    if (DERIV) {
+      group_reduce4<T, G>(val, du0, du1, du2, lane);
+    } else {
 #pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-      val += __shfl_xor_sync(0xffffffffu, val, off, G);
-      if (DERIV) {
-        du0 += __shfl_xor_sync(0xffffffffu, du0, off, G);
-        du1 += __shfl_xor_sync(0xffffffffu, du1, off, G);
-        du2 += __shfl_xor_sync(0xffffffffu, du2, off, G);
-      }
+      for (int off = G / 2; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off, G);
     }
     if (lane == 0 && valid) {
       if (MODE & 1) {
@@ -217,16 +288,24 @@ gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
 // ---------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------
+template <typename T>
+static MeshDims<T> make_dims(int nx, int ny, int nz) {
+  MeshDims<T> d;
+  d.n[0] = nx; d.n[1] = ny; d.n[2] = nz;
+  d.inv_n[0] = T(1) / T(nx); d.inv_n[1] = T(1) / T(ny); d.inv_n[2] = T(1) / T(nz);
+  return d;
+}
+
 template <typename T, int METHOD, int N>
 int launch_spread(const void* positions, const void* weights, int64_t n_points, int n_channels,
                   const double* r2u, int nx, int ny, int nz, void* mesh, cudaStream_t stream) {
-  const int64_t threads = n_points * N * N;
+  const int64_t threads = n_points * GroupSize<N>::value;  // one lane per (point, z offset)
   const int block = 256;
   const int64_t grid = (threads + block - 1) / block;
   if (grid == 0) return 0;
   spread_kernel<T, METHOD, N><<<(unsigned)grid, block, 0, stream>>>(
-      (const T*)positions, (const T*)weights, n_points, n_channels, load_mat3<T>(r2u), nx, ny, nz,
-      (T*)mesh);
+      (const T*)positions, (const T*)weights, n_points, n_channels, load_mat3<T>(r2u),
+      make_dims<T>(nx, ny, nz), (T*)mesh);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -255,8 +334,8 @@ int launch_gather(const void* mesh, const void* positions, const void* coef, int
   if (grid == 0) return 0;
   gather_kernel<T, METHOD, N, MODE><<<(unsigned)grid, block, 0, stream>>>(
       (const T*)mesh, (const T*)positions, (const T*)coef, n_points, n_channels,
-      load_mat3<T>(r2u), nx, ny, nz, (T*)values, (T*)dvalues, (T*)grad_positions, accumulate,
-      (T*)grad_r2u, epi);
+      load_mat3<T>(r2u), make_dims<T>(nx, ny, nz), (T*)values, (T*)dvalues, (T*)grad_positions,
+      accumulate, (T*)grad_r2u, epi);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
