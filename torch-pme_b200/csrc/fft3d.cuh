@@ -229,6 +229,10 @@ __device__ __forceinline__ int freq_index(int i, int n) { return i < (n + 1) / 2
 // inner (z) elements.  MODE 0: forward, 1: inverse, 2: forward . G . inverse (x pass only).
 // Tile origin of work item `o`: (o / d1) * s1 + (o % d1) * s0 + chunk * zc; line stride `ls`.
 // ---------------------------------------------------------------------------------------
+// skewed position inside a row buffer: one pad element every 16, so that the stride-RL accesses of
+// the second radix group fall into distinct shared-memory banks
+__device__ __forceinline__ int skew(int p) { return p + (p >> 4); }
+
 template <typename T> struct MaxThreads { static constexpr int value = sizeof(T) == 8 ? 128 : 256; };
 
 template <typename T, typename GT, int N, int MODE, int GV>
@@ -413,8 +417,9 @@ rows_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int64_t n_row
   constexpr int NG = CH::NG, RA = CH::RA, RL = CH::RL, QA = H / RA;
   static_assert(NG <= 2, "row transforms use at most two radix groups");
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int P1 = H + (H >> 4) + 1;   // pitch of the skewed exchange buffer
   C2<T>* buf1 = reinterpret_cast<C2<T>*>(smem_raw);
-  C2<T>* buf2 = buf1 + (NG == 2 ? (size_t)rows_per_cta * P : 0);
+  C2<T>* buf2 = buf1 + (NG == 2 ? (size_t)rows_per_cta * P1 : 0);
   C2<T>* tw = buf2 + (size_t)rows_per_cta * P;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -433,7 +438,7 @@ rows_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int64_t n_row
       for (int i = 0; i < RA; ++i) buf2[r * P + bitrev<H>(i)] = v[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < RA; ++i) buf1[r * P + j0 + i * QA] = v[i];
+      for (int i = 0; i < RA; ++i) buf1[r * P1 + skew(j0 + i * QA)] = v[i];
     }
   }
   __syncthreads();
@@ -442,7 +447,7 @@ rows_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int64_t n_row
       const int r = w / (H / RL), blk = w - r * (H / RL);
       C2<T> v[RL];
 #pragma unroll
-      for (int i = 0; i < RL; ++i) v[i] = buf1[r * P + blk * RL + i];
+      for (int i = 0; i < RL; ++i) v[i] = buf1[r * P1 + skew(blk * RL + i)];
       dif_regs<T, H, RL, RL, -1, 2>(v, 0, tw);
 #pragma unroll
       for (int i = 0; i < RL; ++i) buf2[r * P + bitrev<H>(blk * RL + i)] = v[i];
@@ -489,8 +494,9 @@ rows_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int64_t n_row
   constexpr int NG = CH::NG, RA = CH::RA, RL = CH::RL, QA = H / RA;
   static_assert(NG <= 2, "row transforms use at most two radix groups");
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int P1 = H + (H >> 4) + 1;   // pitch of the skewed exchange buffer
   C2<T>* buf1 = reinterpret_cast<C2<T>*>(smem_raw);
-  C2<T>* buf2 = buf1 + (NG == 2 ? (size_t)rows_per_cta * P : 0);
+  C2<T>* buf2 = buf1 + (NG == 2 ? (size_t)rows_per_cta * P1 : 0);
   C2<T>* tw = buf2 + (size_t)rows_per_cta * P;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -546,14 +552,14 @@ rows_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int64_t n_row
     for (int i = 0; i < RL; ++i) v[i] = buf2[r * P + bitrev<H>(blk * RL + i)];
     dit_regs<T, H, 1, RL, +1, 2>(v, 0, tw);
 #pragma unroll
-    for (int i = 0; i < RL; ++i) buf1[r * P + blk * RL + i] = v[i];
+    for (int i = 0; i < RL; ++i) buf1[r * P1 + skew(blk * RL + i)] = v[i];
   }
   __syncthreads();
   for (int w = tid; w < rows * QA; w += nt) {
     const int r = w / QA, j0 = w - r * QA;
     C2<T> v[RA];
 #pragma unroll
-    for (int i = 0; i < RA; ++i) v[i] = buf1[r * P + j0 + i * QA];
+    for (int i = 0; i < RA; ++i) v[i] = buf1[r * P1 + skew(j0 + i * QA)];
     dit_regs<T, H, QA, RA, +1, 2>(v, j0, tw);
 #pragma unroll
     for (int i = 0; i < RA; ++i) o[(int64_t)r * H + j0 + i * QA] = v[i];   // (y[2m], y[2m+1])
@@ -584,7 +590,7 @@ int launch_rows(bool forward, const void* in, void* out, int64_t n_rows, cudaStr
   const int64_t grid = (n_rows + rows - 1) / rows;
   int threads = rows * items_per_row;
   threads = threads < 64 ? 64 : (threads > 256 ? 256 : (threads + 31) / 32 * 32);
-  const size_t smem = ((size_t)rows * P * Chain<H>::NG + NZ / 2) * sizeof(C2<T>);
+  const size_t smem = ((size_t)rows * (P + (Chain<H>::NG == 2 ? H + (H >> 4) + 1 : 0)) + NZ / 2) * sizeof(C2<T>);
   if (forward) {
     if (int rc = allow_smem(rows_r2c_kernel<T, NZ>, smem)) return rc;
     rows_r2c_kernel<T, NZ><<<(unsigned)grid, threads, smem, s>>>((const T*)in, (C2<T>*)out, n_rows, rows);
