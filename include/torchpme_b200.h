@@ -84,8 +84,9 @@ typedef struct tpme_fft_plan_s* tpme_fft_plan;
 
 int tpme_fft_plan_create(tpme_fft_plan* plan, int dtype, int nx, int ny, int nz, int batch);
 int tpme_fft_plan_destroy(tpme_fft_plan plan);
-/* 1 if tpme_kfilter_apply runs the hand-written fused FFT . G . iFFT for this plan (all mesh
- * dimensions powers of two in 8..512), 0 if it goes through cuFFT + a multiply kernel */
+/* number of hand-written kernels tpme_kfilter_apply launches for this plan (all mesh dimensions
+ * powers of two in 8..512): 3 (fused (y,z)-plane passes + x pass with G), 5 (separate z / y / x
+ * passes); 0 if it goes through cuFFT + a multiply kernel */
 int tpme_fft_plan_uses_own_fft(tpme_fft_plan plan);
 /* unnormalised forward / inverse real 3-D transforms over the last three axes */
 int tpme_rfft3(tpme_fft_plan plan, const void* mesh, void* mesh_hat, void* stream);

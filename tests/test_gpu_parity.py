@@ -166,7 +166,8 @@ def test_against_oracle_synthetic(config):
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("ns", [(8, 8, 8), (8, 16, 32), (64, 64, 64), (32, 128, 64), (256, 8, 16), (16, 8, 512),
-                                (128, 128, 128), (512, 16, 8)])
+                                (128, 128, 128), (512, 16, 8), (16, 16, 16), (32, 32, 32), (8, 64, 128), (16, 32, 16),
+                                (64, 256, 256)])
 def test_handwritten_fft_filter_matches_torch_fft(ns, dtype):
     """
     The fused FFT . G . iFFT passes (power-of-two meshes) against torch.fft with the same Green's
@@ -181,7 +182,7 @@ def test_handwritten_fft_filter_matches_torch_fft(ns, dtype):
     geom = geometry_of(cell)
     mesh = torch.randn((2,) + ns, generator=gen, dtype=torch.float64).to(dev)
     plan = _native.get_plan(dtype, ns, 2, mesh.device)
-    assert _native.load().tpme_fft_plan_uses_own_fft(plan.handle) == 1
+    assert _native.load().tpme_fft_plan_uses_own_fft(plan.handle) in (3, 5)
     for kind, expo, p3m in ((_native.GREEN_COULOMB, 1, 0), (_native.GREEN_COULOMB, 1, 4), (_native.GREEN_IPL, 6, 0)):
         green = _native.make_green(kind, 0.37, geom.recip, geom.spacing(ns), smearing=1.1, prefactor=1.3,
                                    exponent=expo, p3m_nodes=p3m)

@@ -567,6 +567,225 @@ rows_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int64_t n_row
 }
 
 // ---------------------------------------------------------------------------------------
+// fused (y, z) plane transforms: one CTA per (channel, x) plane keeps the whole half-complex
+// plane [NY][NZ/2+1] in shared memory, so the z and y passes cost one global read and one global
+// write in total (used when the plane fits: <= 128 x 128 here).
+// ---------------------------------------------------------------------------------------
+template <typename T, int NY, int NZ>
+__global__ void __launch_bounds__(MaxThreads<T>::value)
+plane_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int rows_per_chunk) {
+  constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1;
+  using CZ = Chain<H>;
+  using CY = Chain<NY>;
+  static_assert(CZ::NG <= 2 && CY::NG <= 2, "plane kernels use at most two radix groups per axis");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C2<T>* plane = reinterpret_cast<C2<T>*>(smem_raw);
+  C2<T>* buf1 = plane + (size_t)NY * P;
+  C2<T>* twz = buf1 + (CZ::NG == 2 ? (size_t)rows_per_chunk * P1 : 0);
+  C2<T>* twy = twz + NZ / 2;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  fill_twiddles<T, NZ>(twz, tid, nt);
+  fill_twiddles<T, NY>(twy, tid, nt);
+  __syncthreads();
+  const C2<T>* in2 = reinterpret_cast<const C2<T>*>(in) + (int64_t)blockIdx.x * NY * H;
+  // ---- z pass (packed half-length DIF, natural order into the plane) -----------------------
+  constexpr int QAz = H / CZ::RA;
+  for (int row0 = 0; row0 < NY; row0 += rows_per_chunk) {
+    const int rows = min(rows_per_chunk, NY - row0);
+    for (int w = tid; w < rows * QAz; w += nt) {
+      const int r = w / QAz, j0 = w - r * QAz;
+      C2<T> v[CZ::RA];
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) v[i] = in2[(row0 + r) * H + j0 + i * QAz];
+      dif_regs<T, H, H, CZ::RA, -1, 2>(v, j0, twz);
+      if (CZ::NG == 1) {
+#pragma unroll
+        for (int i = 0; i < CZ::RA; ++i) plane[(row0 + r) * P + bitrev<H>(i)] = v[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < CZ::RA; ++i) buf1[r * P1 + skew(j0 + i * QAz)] = v[i];
+      }
+    }
+    __syncthreads();
+    if (CZ::NG == 2) {
+      constexpr int RL = CZ::RL;
+      for (int w = tid; w < rows * (H / RL); w += nt) {
+        const int r = w / (H / RL), blk = w - r * (H / RL);
+        C2<T> v[RL];
+#pragma unroll
+        for (int i = 0; i < RL; ++i) v[i] = buf1[r * P1 + skew(blk * RL + i)];
+        dif_regs<T, H, RL, RL, -1, 2>(v, 0, twz);
+#pragma unroll
+        for (int i = 0; i < RL; ++i) plane[(row0 + r) * P + bitrev<H>(blk * RL + i)] = v[i];
+      }
+      __syncthreads();
+    }
+  }
+  // ---- split in place -------------------------------------------------------------------
+  for (int i = tid; i < NY * (H / 2 + 1); i += nt) {
+    const int r = i / (H / 2 + 1), k = i - r * (H / 2 + 1);
+    C2<T>* row = plane + r * P;
+    if (k == 0) {
+      const C2<T> z0 = row[0];
+      row[0] = {z0.x + z0.y, T(0)};
+      row[H] = {z0.x - z0.y, T(0)};
+    } else {
+      const int kk = H - k;
+      const C2<T> zk = row[k], zkk = row[kk];
+      const C2<T> w = twz[k];
+      {
+        const C2<T> s = {T(0.5) * (zk.x + zkk.x), T(0.5) * (zk.y - zkk.y)};
+        const C2<T> d = {T(0.5) * (zk.x - zkk.x), T(0.5) * (zk.y + zkk.y)};
+        const C2<T> wd = cmul(d, w);
+        row[k] = {s.x + wd.y, s.y - wd.x};
+      }
+      if (kk != k) {
+        const C2<T> s = {T(0.5) * (zkk.x + zk.x), T(0.5) * (zkk.y - zk.y)};
+        const C2<T> d = {T(0.5) * (zkk.x - zk.x), T(0.5) * (zkk.y + zk.y)};
+        const C2<T> wd = {-(d.x * w.x + d.y * w.y), -(d.y * w.x - d.x * w.y)};
+        row[kk] = {s.x + wd.y, s.y - wd.x};
+      }
+    }
+  }
+  __syncthreads();
+  // ---- y pass (DIF along the columns, bit reversal folded into the global line index) -------
+  C2<T>* o = out + (int64_t)blockIdx.x * NY * P;
+  constexpr int QAy = NY / CY::RA;
+  for (int w = tid; w < P * QAy; w += nt) {
+    const int j0 = w / P, c = w - j0 * P;
+    C2<T> v[CY::RA];
+#pragma unroll
+    for (int i = 0; i < CY::RA; ++i) v[i] = plane[(j0 + i * QAy) * P + c];
+    dif_regs<T, NY, NY, CY::RA, -1, 1>(v, j0, twy);
+    if (CY::NG == 1) {
+#pragma unroll
+      for (int i = 0; i < CY::RA; ++i) o[bitrev<NY>(i) * P + c] = v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < CY::RA; ++i) plane[(j0 + i * QAy) * P + c] = v[i];
+    }
+  }
+  if (CY::NG == 1) return;
+  __syncthreads();
+  constexpr int RLy = CY::RL;
+  for (int w = tid; w < P * (NY / RLy); w += nt) {
+    const int blk = w / P, c = w - blk * P;
+    C2<T> v[RLy];
+#pragma unroll
+    for (int i = 0; i < RLy; ++i) v[i] = plane[(blk * RLy + i) * P + c];
+    dif_regs<T, NY, RLy, RLy, -1, 1>(v, 0, twy);
+#pragma unroll
+    for (int i = 0; i < RLy; ++i) o[bitrev<NY>(blk * RLy + i) * P + c] = v[i];
+  }
+}
+
+template <typename T, int NY, int NZ>
+__global__ void __launch_bounds__(MaxThreads<T>::value)
+plane_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int rows_per_chunk) {
+  constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1;
+  using CZ = Chain<H>;
+  using CY = Chain<NY>;
+  static_assert(CZ::NG <= 2 && CY::NG <= 2, "plane kernels use at most two radix groups per axis");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C2<T>* plane = reinterpret_cast<C2<T>*>(smem_raw);
+  C2<T>* buf1 = plane + (size_t)NY * P;
+  C2<T>* twz = buf1 + (CZ::NG == 2 ? (size_t)rows_per_chunk * P1 : 0);
+  C2<T>* twy = twz + NZ / 2;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  fill_twiddles<T, NZ>(twz, tid, nt);
+  fill_twiddles<T, NY>(twy, tid, nt);
+  __syncthreads();
+  const C2<T>* src = in + (int64_t)blockIdx.x * NY * P;
+  // ---- y pass (DIT along the columns; bit-reversed line order read straight from global) ----
+  constexpr int RLy = CY::RL, QAy = NY / CY::RA;
+  for (int w = tid; w < P * (NY / RLy); w += nt) {
+    const int blk = w / P, c = w - blk * P;
+    C2<T> v[RLy];
+#pragma unroll
+    for (int i = 0; i < RLy; ++i) v[i] = src[bitrev<NY>(blk * RLy + i) * P + c];
+    dit_regs<T, NY, 1, RLy, +1, 1>(v, 0, twy);
+#pragma unroll
+    for (int i = 0; i < RLy; ++i) plane[(blk * RLy + i) * P + c] = v[i];
+  }
+  __syncthreads();
+  if (CY::NG == 2) {
+    for (int w = tid; w < P * QAy; w += nt) {
+      const int j0 = w / P, c = w - j0 * P;
+      C2<T> v[CY::RA];
+#pragma unroll
+      for (int i = 0; i < CY::RA; ++i) v[i] = plane[(j0 + i * QAy) * P + c];
+      dit_regs<T, NY, QAy, CY::RA, +1, 1>(v, j0, twy);
+#pragma unroll
+      for (int i = 0; i < CY::RA; ++i) plane[(j0 + i * QAy) * P + c] = v[i];
+    }
+    __syncthreads();
+  }
+  // ---- un-split in place:  Z'[k] = (X[k] + conj X[H-k]) + i conj(w^k) (X[k] - conj X[H-k]) ----
+  for (int i = tid; i < NY * (H / 2 + 1); i += nt) {
+    const int r = i / (H / 2 + 1), k = i - r * (H / 2 + 1);
+    C2<T>* row = plane + r * P;
+    if (k == 0) {
+      const T x0 = row[0].x, xh = row[H].x;
+      row[0] = {x0 + xh, x0 - xh};
+    } else {
+      const int kk = H - k;
+      const C2<T> xk = row[k], xkk = row[kk];
+      const C2<T> w = twz[k];
+      {
+        const C2<T> s = {xk.x + xkk.x, xk.y - xkk.y};
+        const C2<T> d = {xk.x - xkk.x, xk.y + xkk.y};
+        const C2<T> wd = {d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y};
+        row[k] = {s.x - wd.y, s.y + wd.x};
+      }
+      if (kk != k) {
+        const C2<T> s = {xkk.x + xk.x, xkk.y - xk.y};
+        const C2<T> d = {xkk.x - xk.x, xkk.y + xk.y};
+        const C2<T> wd = {-(d.x * w.x - d.y * w.y), -(d.x * w.y + d.y * w.x)};
+        row[kk] = {s.x - wd.y, s.y + wd.x};
+      }
+    }
+  }
+  __syncthreads();
+  // ---- z pass (packed half-length DIT) -------------------------------------------------------
+  C2<T>* o = reinterpret_cast<C2<T>*>(out) + (int64_t)blockIdx.x * NY * H;
+  constexpr int RLz = CZ::RL, QAz = H / CZ::RA;
+  if (CZ::NG == 1) {
+    for (int r = tid; r < NY; r += nt) {
+      C2<T> v[CZ::RA];
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) v[i] = plane[r * P + bitrev<H>(i)];
+      dit_regs<T, H, 1, CZ::RA, +1, 2>(v, 0, twz);
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) o[r * H + i] = v[i];
+    }
+    return;
+  }
+  for (int row0 = 0; row0 < NY; row0 += rows_per_chunk) {
+    const int rows = min(rows_per_chunk, NY - row0);
+    for (int w = tid; w < rows * (H / RLz); w += nt) {
+      const int r = w / (H / RLz), blk = w - r * (H / RLz);
+      C2<T> v[RLz];
+#pragma unroll
+      for (int i = 0; i < RLz; ++i) v[i] = plane[(row0 + r) * P + bitrev<H>(blk * RLz + i)];
+      dit_regs<T, H, 1, RLz, +1, 2>(v, 0, twz);
+#pragma unroll
+      for (int i = 0; i < RLz; ++i) buf1[r * P1 + skew(blk * RLz + i)] = v[i];
+    }
+    __syncthreads();
+    for (int w = tid; w < rows * QAz; w += nt) {
+      const int r = w / QAz, j0 = w - r * QAz;
+      C2<T> v[CZ::RA];
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) v[i] = buf1[r * P1 + skew(j0 + i * QAz)];
+      dit_regs<T, H, QAz, CZ::RA, +1, 2>(v, j0, twz);
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) o[(row0 + r) * H + j0 + i * QAz] = v[i];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 inline bool supported_dim(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
@@ -657,6 +876,37 @@ int dispatch_lines(int n, void* data, int n_outer, int n_inner, int64_t ls, int 
   return 3;
 }
 
+// fused (y, z) plane passes; returns -1 when the plane does not fit (caller falls back)
+template <typename T, int NY, int NZ>
+int launch_plane(bool forward, const void* in, void* out, int n_planes, cudaStream_t s) {
+  constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1;
+  constexpr int threads = MaxThreads<T>::value;
+  constexpr int items_per_row = H / Chain<H>::RA > 0 ? H / Chain<H>::RA : 1;
+  int rows = threads / items_per_row;
+  if (rows < 1) rows = 1;
+  if (rows > NY) rows = NY;
+  const size_t smem = ((size_t)NY * P + (Chain<H>::NG == 2 ? (size_t)rows * P1 : 0) + NZ / 2 + NY / 2) * sizeof(C2<T>);
+  if (smem > 200 * 1024) return -1;
+  if (forward) {
+    if (int rc = allow_smem(plane_r2c_kernel<T, NY, NZ>, smem)) return rc;
+    plane_r2c_kernel<T, NY, NZ><<<n_planes, threads, smem, s>>>((const T*)in, (C2<T>*)out, rows);
+  } else {
+    if (int rc = allow_smem(plane_c2r_kernel<T, NY, NZ>, smem)) return rc;
+    plane_c2r_kernel<T, NY, NZ><<<n_planes, threads, smem, s>>>((const C2<T>*)in, (T*)out, rows);
+  }
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int dispatch_plane(int ny, int nz, bool forward, const void* in, void* out, int n_planes, cudaStream_t s) {
+#define TPME_PLANE(A, B) if (ny == A && nz == B) return launch_plane<T, A, B>(forward, in, out, n_planes, s);
+  TPME_PLANE(16, 16) TPME_PLANE(32, 32) TPME_PLANE(64, 64) TPME_PLANE(128, 128)
+  TPME_PLANE(32, 16) TPME_PLANE(16, 32) TPME_PLANE(64, 32) TPME_PLANE(32, 64) TPME_PLANE(128, 64) TPME_PLANE(64, 128)
+#undef TPME_PLANE
+  return -1;
+}
+
 // which Green variant the x pass can use for this filter
 template <typename GT>
 int green_variant(const GreenDev<GT>& g) {
@@ -679,10 +929,15 @@ int filter_pow2(const void* in, void* out, void* hat, int channels, int nx, int 
   const int gv = FAST ? green_variant(green) : (int)GV_GENERIC;
   // the fast variants evaluate amp * exp(-c k^2) / k^2; the p = 1 power law carries 1 / (c k^2)
   if (gv != GV_GENERIC && green.kind == 2) green.amplitude = green.amplitude / green.half_s2;
-  if (int rc = dispatch_rows<T>(nz, true, in, hat, rows, s)) return rc;
-  // y pass: outer = (c, x), line stride nzh
-  if (int rc = dispatch_lines<T, GT, 0, GV_GENERIC>(ny, hat, channels * nx, nzh, nzh, 1 << 30, 0,
-                                                    (int64_t)ny * nzh, green, nx, ny, nz, nullptr, s)) return rc;
+  // (y, z) passes: fused per-plane kernel when the plane fits in shared memory
+  int prc = dispatch_plane<T>(ny, nz, true, in, hat, channels * nx, s);
+  if (prc > 0) return prc;
+  if (prc < 0) {
+    if (int rc = dispatch_rows<T>(nz, true, in, hat, rows, s)) return rc;
+    // y pass: outer = (c, x), line stride nzh
+    if (int rc = dispatch_lines<T, GT, 0, GV_GENERIC>(ny, hat, channels * nx, nzh, nzh, 1 << 30, 0,
+                                                      (int64_t)ny * nzh, green, nx, ny, nz, nullptr, s)) return rc;
+  }
   // x pass fused with G: outer = (c, y), line stride ny * nzh
   int rc = 0;
 #define TPME_XPASS(GV)                                                                           \
@@ -694,6 +949,8 @@ int filter_pow2(const void* in, void* out, void* hat, int channels, int nx, int 
   else TPME_XPASS(GV_GENERIC);
 #undef TPME_XPASS
   if (rc) return rc;
+  prc = dispatch_plane<T>(ny, nz, false, hat, out, channels * nx, s);
+  if (prc >= 0) return prc;
   if ((rc = dispatch_lines<T, GT, 1, GV_GENERIC>(ny, hat, channels * nx, nzh, nzh, 1 << 30, 0,
                                                  (int64_t)ny * nzh, green, nx, ny, nz, nullptr, s))) return rc;
   return dispatch_rows<T>(nz, false, hat, out, rows, s);

@@ -146,7 +146,15 @@ extern "C" int tpme_fft_plan_create(tpme_fft_plan* plan, int dtype, int nx, int 
   return 0;
 }
 
-extern "C" int tpme_fft_plan_uses_own_fft(tpme_fft_plan plan) { return plan != nullptr && plan->own_fft; }
+// number of our kernels one tpme_kfilter_apply launches for this plan: 0 = cuFFT path (+ the
+// multiply kernel), 3 = fused (y,z)-plane passes + x pass, 5 = separate z / y / x passes
+extern "C" int tpme_fft_plan_uses_own_fft(tpme_fft_plan plan) {
+  if (plan == nullptr || !plan->own_fft) return 0;
+  auto listed = [](int n) { return n == 16 || n == 32 || n == 64 || n == 128; };
+  const int ny = plan->ny, nz = plan->nz;
+  const bool fused = listed(ny) && listed(nz) && (ny == nz || ny == 2 * nz || nz == 2 * ny);
+  return fused ? 3 : 5;
+}
 
 extern "C" int tpme_fft_plan_destroy(tpme_fft_plan plan) {
   if (!plan) return 0;

@@ -272,6 +272,7 @@ class FFTPlan:
             _check(lib.tpme_fft_plan_create(ctypes.byref(handle), 0 if dtype == torch.float32 else 1,
                                             *self.ns, self.batch), "tpme_fft_plan_create")
         self.handle = handle
+        self.own_fft = int(lib.tpme_fft_plan_uses_own_fft(handle))  # 0 (cuFFT), 3 or 5 kernels
 
     def __del__(self):
         try:
@@ -326,7 +327,9 @@ def kfilter_apply(mesh, green: _Green, keep_hat=False, want_dc=False):
         _check(lib.tpme_kfilter_apply(plan.handle, _dev(mesh, "mesh_values"), _dev(out, "out"),
                                       _dev(work, "work"), _dev(kept, "keep"), ctypes.byref(green),
                                       _dev(dc, "dc"), _stream()), "tpme_kfilter_apply")
-    _count()  # Green multiply (the cuFFT kernels are library launches)
+    # hand-written path: rows R2C, y lines, x lines . G, y lines, rows C2R (5 of our kernels);
+    # cuFFT path: our Green multiply only (the cuFFT kernels are library launches)
+    _count(plan.own_fft if plan.own_fft and not keep_hat else 1)
     if want_dc:
         return out, kept, dc
     return out, kept
@@ -404,13 +407,16 @@ def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot:
 
 
 def pair_backward(charges, idx, dist, pair_values, mask_u8, grad_out, full_list: bool,
-                  pot: _PairPotential, want_charges=True, want_pairs=True, grad_charges_out=None):
+                  pot: _PairPotential, want_charges=True, want_pairs=True, grad_charges_out=None,
+                  grad_pairs_out=None):
     lib = load()
     n, c = charges.shape
     g_q = grad_charges_out
     if g_q is None and want_charges:
         g_q = torch.zeros_like(charges)
-    g_p = torch.empty(idx.shape[0], dtype=charges.dtype, device=charges.device) if want_pairs else None
+    g_p = grad_pairs_out
+    if g_p is None and want_pairs:
+        g_p = torch.empty(idx.shape[0], dtype=charges.dtype, device=charges.device)
     with _on(charges, "charges"):
         _check(lib.tpme_pair_backward(_dtype_id(charges), _dev(charges, "charges"),
                                       _dev(idx, "neighbor_indices"), _index_args(idx),

@@ -45,6 +45,18 @@ class _PairSum(torch.autograd.Function):
         return g_q, g_x, None, None, None, None
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """one auxiliary stream per device for work that is independent of the mesh pipeline"""
+    key = torch.device(device).index
+    stream = _side_streams.get(key)
+    if stream is None:
+        stream = _side_streams[key] = torch.cuda.Stream(device=device)
+    return stream
+
+
 class _FusedStepConfig:
     """by-value launch parameters of one fused PME / P3M evaluation"""
     __slots__ = ("r2u", "ns", "nodes", "method", "green_args", "pair_pot", "full_list",
@@ -71,10 +83,17 @@ class _FusedMeshPotential(torch.autograd.Function):
         idx = neighbor_indices.contiguous()
         need_pos = ctx.needs_input_grad[1]
         out = torch.zeros_like(q)
-        _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
+        # the pair sum is independent of the mesh pipeline until the gather epilogue: run it on a
+        # side stream (a parallel branch when the step is captured in a CUDA graph)
+        main = torch.cuda.current_stream()
+        side = _side_stream(q.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
         rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
         green = _native.make_green(scale=1.0, **cfg.green_args)
         phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
+        main.wait_stream(side)
         epi = _native.make_epilogue(q, dc, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume)
         _, dvalues = _native.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=need_pos,
                                     values_out=out, epilogue=epi)
@@ -91,14 +110,27 @@ class _FusedMeshPotential(torch.autograd.Function):
         g = grad_out.contiguous()
         g_q = torch.zeros_like(q) if need_q else None
         g_d = None
+        main = torch.cuda.current_stream()
+        side = _side_stream(q.device)
+        forked = False
         if need_q or need_d:
-            _, g_d = _native.pair_backward(q, idx, d, None, mask_u8, g, cfg.full_list, cfg.pair_pot,
-                                           want_charges=need_q, want_pairs=need_d, grad_charges_out=g_q)
+            # dL/dd is produced by the pair kernel alone -> side stream; when dL/dq is wanted too the
+            # gather epilogue accumulates into the same buffer, so the join happens before it
+            g_d = torch.empty(idx.shape[0], dtype=q.dtype, device=q.device) if need_d else None
+            side.wait_stream(main)
+            forked = True
+            with torch.cuda.stream(side):
+                _native.pair_backward(q, idx, d, None, mask_u8, g, cfg.full_list, cfg.pair_pot,
+                                      want_charges=need_q, want_pairs=need_d, grad_charges_out=g_q,
+                                      grad_pairs_out=g_d)
         g_pos = None
         if need_q or need_pos:
             rho_g = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
             green = _native.make_green(scale=1.0, **cfg.green_args)
             psi, _, dc_g = _native.kfilter_apply(rho_g, green, want_dc=True)
+            if forked and need_q:
+                main.wait_stream(side)
+                forked = False
             epi = _native.make_epilogue(g, dc_g, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume,
                                         coef2=g if need_pos else None, dvalues2=dvalues,
                                         vjp_scale=cfg.half_ivolume)
@@ -107,6 +139,8 @@ class _FusedMeshPotential(torch.autograd.Function):
                                                  values_out=g_q, epilogue=epi)
             else:
                 _native.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi)
+        if forked:
+            main.wait_stream(side)
         return g_q, g_pos, g_d, None, None, None
 
 
@@ -201,6 +235,11 @@ class PMECalculator(Calculator):
                                    periodic, node_mask, pair_mask, kvectors)
         validate_parameters(charges, cell, positions, neighbor_indices, neighbor_distances,
                             periodic, pair_mask, node_mask, kvectors)
+        if not positions.is_cuda:
+            raise _native.NativeLibraryError(
+                f"`positions` lives on {positions.device}; torchpme_b200 is a CUDA-only implementation "
+                "(no CPU fallback). Move the inputs to a CUDA device."
+            )
         pot = self.potential
         geom = geometry_of(cell)
         ns = geom.ns_mesh(self.mesh_spacing)
