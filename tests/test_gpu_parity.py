@@ -123,7 +123,7 @@ def test_block_golden():
         tab = _native.green_table(dt, nsh, green, cell.device)
         assert rel_err(tab.cpu(), g[f"kfilter_ipl{p}"]) < 1e-11, p
         green32 = _native.green_table(torch.float32, nsh, green, cell.device)
-        assert rel_err(green32.cpu(), g[f"kfilter_ipl{p}"]) < 1e-5, p
+        assert rel_err(green32.cpu(), g[f"kfilter_ipl{p}"]) < 1e-4, p
 
 
 @pytest.mark.parametrize("config", ["c2", "c3_small", "c5_small"])
@@ -192,3 +192,30 @@ def test_handwritten_fft_filter_matches_torch_fft(ns, dtype):
         tol = 1e-11 if dtype == torch.float64 else 2e-5
         assert rel_err(out, ref) < tol, (kind, expo, p3m)
         assert rel_err(dc, mesh.sum(dim=(1, 2, 3))) < (1e-10 if dtype == torch.float64 else 1e-3)
+
+
+def test_graphed_step_matches_eager():
+    """torchpme_b200.GraphedStep (CUDA-graph replay over static buffers) against the eager call."""
+    import torchpme_b200 as tp
+
+    pos, q, cell, idx, d = rocksalt(8, dtype=torch.float32, device="cuda")
+    L = float(cell[0, 0])
+    calc = tp.P3MCalculator(tp.CoulombPotential(smearing=1.2).to("cuda"), mesh_spacing=L / 6)
+    p = pos.clone().requires_grad_(True)
+    dd = d.clone().requires_grad_(True)
+    V = calc(q, cell, p, idx, dd)
+    e_ref = (V * q).sum()
+    gp_ref, gd_ref = torch.autograd.grad(e_ref, (p, dd))
+    graphed = tp.GraphedStep(calc, q, cell, pos, idx, d)
+    for shift in (0.0, 0.05):          # second call: new positions copied into the static buffers
+        new_pos = pos + shift
+        e, gp, gd = graphed(positions=new_pos.cpu().pin_memory())
+        p2 = new_pos.clone().requires_grad_(True)
+        d2 = d.clone().requires_grad_(True)
+        V2 = calc(q, cell, p2, idx, d2)
+        e2 = (V2 * q).sum()
+        gp2, gd2 = torch.autograd.grad(e2, (p2, d2))
+        torch.cuda.synchronize()
+        assert rel_err(e, e2.detach()) < 1e-5
+        assert rel_err(gp, gp2) < 1e-4
+        assert rel_err(gd, gd2) < 1e-5

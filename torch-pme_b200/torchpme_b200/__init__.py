@@ -9,9 +9,10 @@ Only the hot path of the reference is provided: PME / P3M 
 Coulomb and inverse-power-law potentials, the mesh interpolator and k-space filter blocks.
 """
 
-from . import calculators, lib, mesh, potentials, prefactors  # noqa: F401
+from . import calculators, graphs, lib, mesh, potentials, prefactors  # noqa: F401
 from ._native import NativeLibraryError, library_path  # noqa: F401
 from .calculators import Calculator, P3MCalculator, PMECalculator
+from .graphs import GraphedStep  # noqa: F401
 from .mesh import set_nan_check  # noqa: F401
 from .potentials import CoulombPotential, InversePowerLawPotential, Potential
 
