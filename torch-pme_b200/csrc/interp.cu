@@ -163,7 +163,7 @@ __device__ __forceinline__ void group_reduce4(T& q0, T& q1, T& q2, T& q3, int la
 }
 
 template <typename T, int METHOD, int N, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (N <= 4 && sizeof(T) == 4) ? 4 : 2)
 gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
               const T* __restrict__ coef, int64_t n_points, int n_channels, Mat3<T> r2u,
               MeshDims<T> dims, T* __restrict__ values, T* __restrict__ dvalues,

@@ -5,6 +5,8 @@
 // The short-range kernel is evaluated in its cancellation-free closed form
 // Q(p/2, d^2 / 2 s^2) / d^p instead of "full - long range"
 // (coulomb.py:80-120, inversepowerlaw.py:54-106).
+#include <cmath>
+
 #include "common.cuh"
 #include "../../include/torchpme_b200.h"
 
@@ -92,6 +94,85 @@ __device__ __forceinline__ void short_range(const PairPot<T>& pp, T d, T& v, T& 
   dv = pp.prefactor * dsr;
 }
 
+// Fast path: plain 1/r (Coulomb or p = 1 power law), no exclusion zone.
+//   v = pref erfc(a d) / d,   dv/dd = -(v + pref 2a/sqrt(pi) exp(-a^2 d^2)) / d,   a = 1/(s sqrt 2)
+template <typename T> struct PairFast;
+template <> struct PairFast<float> {
+  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+  static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+};
+template <> struct PairFast<double> {
+  static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+  static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+};
+
+template <typename T, bool DERIV>
+__device__ __forceinline__ void coulomb_short_range(T a, T pref, T d, T& v, T& dv) {
+  const T ad = a * d;
+  const T inv_d = PairFast<T>::rcp(d);
+  v = pref * erfc_t(ad) * inv_d;
+  if (DERIV)
+    dv = -(v + pref * T(1.1283791670955125739) * a * PairFast<T>::exp(-ad * ad)) * inv_d;
+}
+
+template <typename I> struct IndexPair;
+template <> struct IndexPair<int64_t> {
+  static __device__ __forceinline__ void load(const int64_t* idx, int64_t p, int64_t& i, int64_t& j) {
+    const longlong2 v = *reinterpret_cast<const longlong2*>(idx + 2 * p);
+    i = v.x; j = v.y;
+  }
+};
+template <> struct IndexPair<int32_t> {
+  static __device__ __forceinline__ void load(const int32_t* idx, int64_t p, int64_t& i, int64_t& j) {
+    const int2 v = *reinterpret_cast<const int2*>(idx + 2 * p);
+    i = v.x; j = v.y;
+  }
+};
+
+// single-channel Coulomb-type potential: the common case, no channel loop, no branches on kind
+template <typename T, typename I, bool HALF>
+__global__ void __launch_bounds__(256)
+pair_forward_coulomb_kernel(const T* __restrict__ charges, const I* __restrict__ idx,
+                            const T* __restrict__ dist, const uint8_t* __restrict__ mask,
+                            int64_t n_pairs, T a, T half_pref, T* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  if (mask != nullptr && mask[p] == 0) return;
+  int64_t i, j;
+  IndexPair<I>::load(idx, p, i, j);
+  T v, dv;
+  coulomb_short_range<T, false>(a, half_pref, dist[p], v, dv);
+  red_add(out + i, __ldg(charges + j) * v);
+  if (HALF) red_add(out + j, __ldg(charges + i) * v);
+}
+
+template <typename T, typename I, bool HALF>
+__global__ void __launch_bounds__(256)
+pair_backward_coulomb_kernel(const T* __restrict__ charges, const I* __restrict__ idx,
+                             const T* __restrict__ dist, const uint8_t* __restrict__ mask,
+                             const T* __restrict__ grad_out, int64_t n_pairs, T a, T half_pref,
+                             T* __restrict__ grad_charges, T* __restrict__ grad_pairs) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  if (mask != nullptr && mask[p] == 0) {
+    if (grad_pairs) grad_pairs[p] = T(0);
+    return;
+  }
+  int64_t i, j;
+  IndexPair<I>::load(idx, p, i, j);
+  T v, dv;
+  coulomb_short_range<T, true>(a, half_pref, dist[p], v, dv);
+  const T gi = __ldg(grad_out + i);
+  T acc = gi * __ldg(charges + j);
+  if (grad_charges) red_add(grad_charges + j, gi * v);
+  if (HALF) {
+    const T gj = __ldg(grad_out + j);
+    acc = fma_t(gj, __ldg(charges + i), acc);
+    if (grad_charges) red_add(grad_charges + i, gj * v);
+  }
+  if (grad_pairs) grad_pairs[p] = acc * dv;
+}
+
 template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 pair_forward_kernel(const T* __restrict__ charges, const I* __restrict__ idx,
@@ -160,6 +241,10 @@ static PairPot<T> make_pair_pot(const tpme_pair_potential* h) {
   return pp;
 }
 
+static bool is_plain_coulomb(const tpme_pair_potential* h) {
+  return (h->kind == 1 || (h->kind == 2 && h->exponent == 1)) && !(h->exclusion_radius > 0);
+}
+
 static int check_pair(const tpme_pair_potential* h, const void* dist, const void* values) {
   TPME_REQUIRE(h != nullptr, "pair potential missing");
   TPME_REQUIRE(h->kind >= 0 && h->kind <= 2, "pair kind must be 0, 1 or 2");
@@ -189,6 +274,19 @@ extern "C" int tpme_pair_forward(int dtype, const void* charges, const void* nei
   if (n_pairs == 0 || n_channels == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((n_pairs + 255) / 256);
+  if (is_plain_coulomb(pot) && n_channels == 1) {
+    const double a = 1.0 / (pot->smearing * sqrt(2.0)), hp = 0.5 * pot->prefactor;
+#define GOC(T, I, H)                                                                                  \
+  pair_forward_coulomb_kernel<T, I, H><<<grid, 256, 0, s>>>((const T*)charges, (const I*)neighbor_indices, \
+      (const T*)distances, pair_mask, n_pairs, (T)a, (T)hp, (T*)out)
+#define GOCI(T, I) do { if (full_neighbor_list) GOC(T, I, false); else GOC(T, I, true); } while (0)
+    if (dtype == 0) { if (index_is_int64) GOCI(float, int64_t); else GOCI(float, int32_t); }
+    else            { if (index_is_int64) GOCI(double, int64_t); else GOCI(double, int32_t); }
+#undef GOCI
+#undef GOC
+    TPME_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
 #define GO(T, I)                                                                              \
   pair_forward_kernel<T, I><<<grid, 256, 0, s>>>((const T*)charges, (const I*)neighbor_indices, \
       (const T*)distances, (const T*)pair_values, pair_mask, n_pairs, n_channels,             \
@@ -213,6 +311,20 @@ extern "C" int tpme_pair_backward(int dtype, const void* charges, const void* ne
   if (n_pairs == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((n_pairs + 255) / 256);
+  if (is_plain_coulomb(pot) && n_channels == 1) {
+    const double a = 1.0 / (pot->smearing * sqrt(2.0)), hp = 0.5 * pot->prefactor;
+#define GOC(T, I, H)                                                                                   \
+  pair_backward_coulomb_kernel<T, I, H><<<grid, 256, 0, s>>>((const T*)charges, (const I*)neighbor_indices, \
+      (const T*)distances, pair_mask, (const T*)grad_out, n_pairs, (T)a, (T)hp, (T*)grad_charges,      \
+      (T*)grad_pairs)
+#define GOCI(T, I) do { if (full_neighbor_list) GOC(T, I, false); else GOC(T, I, true); } while (0)
+    if (dtype == 0) { if (index_is_int64) GOCI(float, int64_t); else GOCI(float, int32_t); }
+    else            { if (index_is_int64) GOCI(double, int64_t); else GOCI(double, int32_t); }
+#undef GOCI
+#undef GOC
+    TPME_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
 #define GO(T, I)                                                                               \
   pair_backward_kernel<T, I><<<grid, 256, 0, s>>>((const T*)charges, (const I*)neighbor_indices, \
       (const T*)distances, (const T*)pair_values, pair_mask, (const T*)grad_out, n_pairs,       \
