@@ -6,8 +6,12 @@ plus dE/d neighbor_distances), on the synthetic rock-salt crystals of SURVEY.md 
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
 
-N > 1 is launched by torchrun, one rank per GPU; every rank runs an independent replica of
-the workload (weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
+N > 1 is launched by torchrun, one rank per GPU.  Default (`--decomposition replica`): every
+rank runs an independent replica of the workload (weak scaling, no data-path collective) --
+the meshes of c2/c3/c5 are too small to shard.  `--decomposition slab` runs ONE system whose
+mesh is cut into x slabs over the ranks (torchpme_b200.distributed: all-to-all FFT transposes
+over NCCL or NVLink peer stores, all-reduced potentials / forces; strong scaling) -- meant for
+c4.  Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -123,13 +127,19 @@ def build_inputs(wl, device):
                 mesh_spacing=mesh_spacing, dtype=dtype)
 
 
-def make_calculator(wl, mesh_spacing, device):
+def make_calculator(wl, mesh_spacing, device, slab_transport=None):
     import torchpme_b200 as tp
 
     if wl["pot"]["kind"] == "coulomb":
         pot = tp.CoulombPotential(smearing=SMEARING)
     else:
         pot = tp.InversePowerLawPotential(exponent=wl["pot"]["exponent"], smearing=SMEARING)
+    if slab_transport is not None:
+        from torchpme_b200.distributed import SlabP3MCalculator, SlabPMECalculator
+        cls = SlabPMECalculator if wl["calc"] == "pme" else SlabP3MCalculator
+        # every rank is handed its own chunk of the pair list (shard_pairs=False)
+        return cls(pot.to(device), mesh_spacing=mesh_spacing, interpolation_nodes=NODES,
+                   transport=slab_transport, shard_pairs=False)
     cls = tp.PMECalculator if wl["calc"] == "pme" else tp.P3MCalculator
     return cls(pot.to(device), mesh_spacing=mesh_spacing, interpolation_nodes=NODES)
 
@@ -197,12 +207,22 @@ def run_b200(args, wl):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    slab = args.decomposition == "slab"
+    if world > 1 or slab:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29555")
+        dist.init_process_group("nccl", device_id=device, rank=rank, world_size=world)
 
     inputs = build_inputs(wl, device)
     dtype = inputs["dtype"]
-    calc = make_calculator(wl, inputs["mesh_spacing"], device)
+    n_pairs_total = inputs["neighbor_indices"].shape[0]
+    if slab:
+        # one system over all ranks: replicated atoms, every rank keeps its chunk of the pair list
+        from torchpme_b200.distributed import SlabLayout
+        lo, hi = SlabLayout((world, world, 2), world, rank).pair_range(n_pairs_total)
+        inputs["neighbor_indices"] = inputs["neighbor_indices"][lo:hi].contiguous()
+        inputs["neighbor_distances"] = inputs["neighbor_distances"][lo:hi].contiguous()
+    calc = make_calculator(wl, inputs["mesh_spacing"], device, args.transport if slab else None)
     q, cell, idx = inputs["charges"], inputs["cell"], inputs["neighbor_indices"]
     pos = inputs["positions"].clone().requires_grad_(True)
     d = inputs["neighbor_distances"].clone().requires_grad_(True)
@@ -220,8 +240,23 @@ def run_b200(args, wl):
         step()
     torch.cuda.synchronize()
     launches_before = _native.launch_counter
-    graphed = tp.GraphedStep(calc, q, cell, inputs["positions"], idx, inputs["neighbor_distances"], warmup=1)
-    launches_per_step = (_native.launch_counter - launches_before) // 2   # 1 warm-up + 1 captured step
+    graph_error = None
+    if args.no_graph:
+        graphed, graph_error = None, "disabled (--no-graph)"
+    else:
+        try:
+            graphed = tp.GraphedStep(calc, q, cell, inputs["positions"], idx, inputs["neighbor_distances"], warmup=1)
+        except Exception as exc:  # e.g. a collective that cannot be captured: time the eager step instead
+            if not slab:
+                raise
+            graphed, graph_error = None, f"{type(exc).__name__}: {exc}"[:300]
+            torch.cuda.synchronize()
+    if graphed is not None:
+        launches_per_step = (_native.launch_counter - launches_before) // 2   # 1 warm-up + 1 captured step
+    else:
+        launches_before = _native.launch_counter
+        step()
+        launches_per_step = _native.launch_counter - launches_before
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
@@ -249,8 +284,8 @@ def run_b200(args, wl):
     if rank == 0:
         sampler.start()
     warm = max(3, args.warmup)
-    graph_ms = timed(graphed.replay, args.steps, warm)
     eager_ms = timed(step, args.steps, warm)
+    graph_ms = timed(graphed.replay, args.steps, warm) if graphed is not None else eager_ms
 
     # ---- end to end through the public API: pinned host inputs -> device, forces -> host ----
     host = {k: inputs[k].detach().cpu().pin_memory() for k in
@@ -268,6 +303,9 @@ def run_b200(args, wl):
         h_forces.copy_(g_pos, non_blocking=True)
         h_energy.copy_(energy, non_blocking=True)
 
+    if graphed is None:
+        e2e_step = None
+
     def e2e_eager_step():
         c_pos = host["positions"].to(device, non_blocking=True).requires_grad_(True)
         c_q = host["charges"].to(device, non_blocking=True)
@@ -280,13 +318,22 @@ def run_b200(args, wl):
         h_forces.copy_(g_pos, non_blocking=True)
         h_energy.copy_(energy.detach(), non_blocking=True)
 
-    e2e_ms = timed(e2e_step, args.steps, warm)
     e2e_eager_ms = timed(e2e_eager_step, args.steps, warm)
+    e2e_ms = timed(e2e_step, args.steps, warm) if e2e_step is not None else e2e_eager_ms
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-stage roofline (rank 0): each stage timed alone, L2 flushed before every launch ----
     roofline, stages = None, None
-    if rank == 0:
+    if rank == 0 and slab:
+        s_bytes = 4 if dtype == torch.float32 else 8
+        alg = algorithmic_bytes(n_atoms, n_pairs_total, wl["n_mesh"], s_bytes)
+        peak, peak_src = measured_peak()
+        step_gbs = sum(alg.values()) / (graph_ms / args.steps) / 1e6
+        roofline = {"bound": "hbm", "kernel": "whole step over all ranks", "achieved": round(step_gbs, 1),
+                    "peak": peak * world, "unit": "GB/s", "frac": round(step_gbs / (peak * world), 4),
+                    "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
+                    "step_alg_bytes": sum(alg.values())}
+    if rank == 0 and not slab:
         from torchpme_b200.mesh import geometry_of
         s = 4 if dtype == torch.float32 else 8
         alg = algorithmic_bytes(n_atoms, n_pairs, wl["n_mesh"], s)
@@ -332,7 +379,7 @@ def run_b200(args, wl):
 
     # ---- CPU baseline (rank 0, N = 1 only): the numpy oracle on a bounded sample ----
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not slab and not args.no_cpu_baseline:
         cpu = {k: inputs[k].detach().cpu().numpy() for k in
                ("positions", "charges", "cell", "neighbor_indices", "neighbor_distances")}
         cpu["mesh_spacing"] = inputs["mesh_spacing"]
@@ -346,19 +393,22 @@ def run_b200(args, wl):
         per_step = graph_ms / args.steps
         line = {
             "metric": "atom-steps/sec (energy+forces)",
-            "value": world * n_atoms * args.steps / (graph_ms * 1e-3),
+            "value": (1 if slab else world) * n_atoms * args.steps / (graph_ms * 1e-3),
             "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": per_step, "higher_is_better": True, "scaling": "strong" if slab else "weak",
+            "vs_baseline": None,
             "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
             "config": {"workload": wl["label"], "atoms": n_atoms, "pairs": n_pairs, "mesh": wl["n_mesh"],
                        "smearing": SMEARING, "cutoff": CUTOFF, "interpolation_nodes": NODES,
                        "step": "forward + backward of sum(q*V) w.r.t. positions and neighbor distances, "
                                "whole step replayed as one CUDA graph",
                        "l2": "flushed (256 MiB write) before every timed step",
-                       "parallelism": "independent replica per GPU" if world > 1 else "single GPU"},
-            "eager": {"value": world * n_atoms * args.steps / (eager_ms * 1e-3), "ms_per_step": eager_ms / args.steps,
+                       "parallelism": (f"one system, mesh slab-decomposed over {world} GPU(s), transport={args.transport}"
+                                       f"{'' if graph_error is None else ', eager launches (' + graph_error + ')'}") if slab
+                       else ("independent replica per GPU" if world > 1 else "single GPU")},
+            "eager": {"value": (1 if slab else world) * n_atoms * args.steps / (eager_ms * 1e-3), "ms_per_step": eager_ms / args.steps,
                       "note": "same step launched from Python without graph capture"},
-            "e2e": {"value": world * n_atoms * args.steps / (e2e_ms * 1e-3), "unit": "atom-steps/s",
+            "e2e": {"value": (1 if slab else world) * n_atoms * args.steps / (e2e_ms * 1e-3), "unit": "atom-steps/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d - host["cell"].numel() * host["cell"].element_size(),
                     "d2h_bytes_per_step": d2h,
                     "path": "torchpme_b200.GraphedStep: pinned host positions/charges/neighbor list copied into the "
@@ -369,7 +419,8 @@ def run_b200(args, wl):
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if world > 1 or slab:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -381,6 +432,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decomposition", default="replica", choices=["replica", "slab"])
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -75,6 +75,25 @@ int tpme_gather_vjp(int dtype, const void* mesh, const void* positions, const vo
                     int accumulate, void* grad_r2u, const tpme_point_epilogue* epilogue,
                     void* stream);
 
+/* Slab variants of the three calls above for a mesh decomposed into x slabs (one per GPU,
+ * SURVEY.md section 8e): `mesh` is the local slab (C, nx_local, ny, nz) holding the planes
+ * x0 .. x0 + nx_local - 1 of the global (nx, ny, nz) mesh.  Stencil nodes outside the slab are
+ * skipped, so spreading needs no halo reduction and the gathers return PARTIAL sums whose sum
+ * over the slabs is the full result (the caller all-reduces them together with the real-space
+ * part).  x0 = 0, nx_local = nx is exactly the plain call. */
+int tpme_spread_slab(int dtype, const void* positions, const void* weights, int64_t n_points,
+                     int n_channels, const double* r2u_host, int nx, int ny, int nz, int x0,
+                     int nx_local, int nodes, int method, void* mesh, int accumulate, void* stream);
+int tpme_gather_slab(int dtype, const void* mesh, const void* positions, int64_t n_points,
+                     int n_channels, const double* r2u_host, int nx, int ny, int nz, int x0,
+                     int nx_local, int nodes, int method, void* values, void* dvalues,
+                     const tpme_point_epilogue* epilogue, void* stream);
+int tpme_gather_vjp_slab(int dtype, const void* mesh, const void* positions, const void* coef,
+                         int64_t n_points, int n_channels, const double* r2u_host, int nx, int ny,
+                         int nz, int x0, int nx_local, int nodes, int method, void* grad_positions,
+                         void* values, int accumulate, void* grad_r2u,
+                         const tpme_point_epilogue* epilogue, void* stream);
+
 /* ---- reciprocal space ---------------------------------------------------------------
  * replaces KSpaceFilter.update + forward and P3MKSpaceFilter
  * (src/torchpme/lib/kspace_filter.py:97-120, 122-197, 293-329),
@@ -125,6 +144,40 @@ int tpme_green_table(int dtype, void* table_out, int nx, int ny, int nz,
  * sum_c Re(x_hat[c,k] * conj(y_hat[c,k])), mult_k = 1 on the kz = 0 / Nyquist planes, 2 else */
 int tpme_green_table_vjp(int dtype, const void* x_hat, const void* y_hat, int n_channels,
                          int nx, int ny, int nz, double scale, void* grad_table, void* stream);
+
+/* ---- slab-decomposed reciprocal space (multi-GPU) -------------------------------------
+ * The 3-D transform of lib/kspace_filter.py:169-187 split at the exchange points of a slab
+ * decomposition (power-of-two mesh dimensions in 8..512):
+ *   tpme_slab_fft_yz       (y,z) passes of `n_planes` = C * nx_local planes; forward:
+ *                          real (n_planes, ny, nz) -> half-complex (n_planes, ny, nz/2+1);
+ *                          otherwise the reverse (the half-complex input is destroyed)
+ *   tpme_slab_fft_x_green  in place on (C, nx, ny_local, nz/2+1), the rows y0 .. y0+ny_local-1:
+ *                          forward x transform, multiply by scale * G(k), inverse x transform
+ *   tpme_slab_exchange_copy  the transposing block copy on either side of the all-to-all:
+ *        dst[p][c * dst_c + a * dst_a + i] = src[c * src_c + p * src_p + a * src_a + i],
+ *        c < n_c, p < n_p, a < n_a, i < run  (strides and run in elements of `elem_bytes`).
+ *        `dst_host` is a host array of n_p device pointers: blocks of a local send buffer, or
+ *        the peers' receive buffers mapped with tpme_peer_buffer_open (NVLink peer stores). */
+#define TPME_MAX_RANKS 16
+#define TPME_IPC_HANDLE_BYTES 64
+int tpme_slab_fft_yz(int dtype, int forward, void* real_mesh, void* mesh_hat, int n_planes, int ny,
+                     int nz, void* stream);
+int tpme_slab_fft_x_green(int dtype, void* mesh_hat_t, int n_channels, int nx, int ny, int nz,
+                          int y0, int ny_local, const tpme_green* green_host, void* stream);
+int tpme_slab_exchange_copy(int elem_bytes, const void* src, void* const* dst_host, int n_c, int n_p,
+                            int n_a, int64_t run, int64_t src_c, int64_t src_p, int64_t src_a,
+                            int64_t dst_c, int64_t dst_a, void* stream);
+/* Peer-memory exchange buffers: cudaMalloc'ed, zero-filled, exported as a CUDA IPC handle that
+ * the other ranks of the node open; and a device-side barrier over uint32 flags[n_ranks] that
+ * live in such a buffer (`flags_host[p]` = rank p's flag array as mapped in this process,
+ * `epoch` = one local uint32, `error_flag` = one local int set when a peer does not arrive
+ * within `timeout_seconds`).  The barrier is CUDA-graph replayable. */
+int tpme_peer_buffer_create(int64_t bytes, void** dev_ptr, unsigned char* handle_out);
+int tpme_peer_buffer_open(const unsigned char* handle, void** dev_ptr);
+int tpme_peer_buffer_close(void* dev_ptr);
+int tpme_peer_buffer_destroy(void* dev_ptr);
+int tpme_peer_barrier(void* const* flags_host, int n_ranks, int rank, void* epoch,
+                      double timeout_seconds, void* error_flag, void* stream);
 
 /* ---- real space -----------------------------------------------------------------------
  * replaces Calculator._compute_rspace (src/torchpme/calculators/calculator.py:43-87) and

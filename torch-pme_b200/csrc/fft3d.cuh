@@ -238,7 +238,8 @@ template <typename T> struct MaxThreads { static constexpr int value = sizeof(T)
 template <typename T, typename GT, int N, int MODE, int GV>
 __global__ void __launch_bounds__(MaxThreads<T>::value)
 lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, int64_t ls, int d1,
-                 int64_t s1, int64_t s0, GreenDev<GT> green, int nx, int ny, int nz, T* __restrict__ dc_out) {
+                 int64_t s1, int64_t s0, GreenDev<GT> green, int nx, int ny, int nz, T* __restrict__ dc_out,
+                 int y_off) {
   using CH = Chain<N>;
   constexpr int NG = CH::NG, RA = CH::RA, RB = CH::RB, RL = CH::RL;
   constexpr int QA = N / RA;                 // element spacing inside the first DIF group
@@ -258,7 +259,7 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
   if (MODE == 2 && GV != GV_GENERIC) {
     for (int i = tid; i < N + cols; i += nt) {
       if (i < N) make_axis_entry<GT, GV>(ax_a[i], green, (GT)freq_index(i, nx), 0, GT(0), -1);
-      else make_axis_entry<GT, GV>(ax_b[i - N], green, (GT)freq_index(o_lo, ny), 1, (GT)(z0 + i - N), 2);
+      else make_axis_entry<GT, GV>(ax_b[i - N], green, (GT)freq_index(o_lo + y_off, ny), 1, (GT)(z0 + i - N), 2);
     }
   }
   if (NG > 1 || MODE == 2) __syncthreads();
@@ -277,14 +278,14 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
           // single-group transform: multiply and invert in the same registers
           AxisEntry<GT> eb;
           if (GV != GV_GENERIC) eb = ax_b[c];
-          if (dc_out != nullptr && o_lo == 0 && z0 + c == 0) dc_out[o_hi] = v[0].x;   // ix = 0
+          if (dc_out != nullptr && o_lo + y_off == 0 && z0 + c == 0) dc_out[o_hi] = v[0].x;   // ix = 0
 #pragma unroll
           for (int i = 0; i < RA; ++i) {
             const int ix = bitrev<N>(i);
             T gv;
             if (GV == GV_GENERIC) {
-              const int64_t flat = ((int64_t)ix * ny + o_lo) * (nz / 2 + 1) + z0 + c;
-              gv = (T)green_value<GT, T>(green, ix, o_lo, z0 + c, nx, ny, nz, flat);
+              const int64_t flat = ((int64_t)ix * ny + o_lo + y_off) * (nz / 2 + 1) + z0 + c;
+              gv = (T)green_value<GT, T>(green, ix, o_lo + y_off, z0 + c, nx, ny, nz, flat);
             } else {
               gv = (T)green_from_axes<GT, GV>(green, ax_a[ix], eb);
             }
@@ -353,14 +354,14 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
       } else {
         AxisEntry<GT> eb;
         if (GV != GV_GENERIC) eb = ax_b[c];
-        if (dc_out != nullptr && blk == 0 && o_lo == 0 && z0 + c == 0) dc_out[o_hi] = v[0].x;   // ix = 0
+        if (dc_out != nullptr && blk == 0 && o_lo + y_off == 0 && z0 + c == 0) dc_out[o_hi] = v[0].x;   // ix = 0
 #pragma unroll
         for (int i = 0; i < RL; ++i) {
           const int ix = bitrev<N>(blk * RL + i);
           T gv;
           if (GV == GV_GENERIC) {
-            const int64_t flat = ((int64_t)ix * ny + o_lo) * (nz / 2 + 1) + z0 + c;
-            gv = (T)green_value<GT, T>(green, ix, o_lo, z0 + c, nx, ny, nz, flat);
+            const int64_t flat = ((int64_t)ix * ny + o_lo + y_off) * (nz / 2 + 1) + z0 + c;
+            gv = (T)green_value<GT, T>(green, ix, o_lo + y_off, z0 + c, nx, ny, nz, flat);
           } else {
             gv = (T)green_from_axes<GT, GV>(green, ax_a[ix], eb);
           }
@@ -838,7 +839,7 @@ int dispatch_rows(int nz, bool forward, const void* in, void* out, int64_t n_row
 
 template <typename T, typename GT, int N, int MODE, int GV>
 int launch_lines(void* data, int n_outer, int n_inner, int64_t ls, int d1, int64_t s1, int64_t s0,
-                 const GreenDev<GT>& green, int nx, int ny, int nz, void* dc_out, cudaStream_t s) {
+                 const GreenDev<GT>& green, int nx, int ny, int nz, void* dc_out, cudaStream_t s, int y_off = 0) {
   // columns per CTA: one first-group radix item per thread, at least ~2 CTAs per SM when the
   // mesh is small, never narrower than 8 columns (64-byte runs)
   constexpr int items_per_col = N / Chain<N>::RA > 0 ? N / Chain<N>::RA : 1;
@@ -858,16 +859,16 @@ int launch_lines(void* data, int n_outer, int n_inner, int64_t ls, int d1, int64
   auto kernel = lines_fft_kernel<T, GT, N, MODE, GV>;
   if (int rc = allow_smem(kernel, smem)) return rc;
   kernel<<<(unsigned)(n_outer * n_chunks), threads, smem, s>>>(
-      (C2<T>*)data, n_inner, zc, n_chunks, ls, d1, s1, s0, green, nx, ny, nz, (T*)dc_out);
+      (C2<T>*)data, n_inner, zc, n_chunks, ls, d1, s1, s0, green, nx, ny, nz, (T*)dc_out, y_off);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <typename T, typename GT, int MODE, int GV>
 int dispatch_lines(int n, void* data, int n_outer, int n_inner, int64_t ls, int d1, int64_t s1, int64_t s0,
-                   const GreenDev<GT>& green, int nx, int ny, int nz, void* dc_out, cudaStream_t s) {
+                   const GreenDev<GT>& green, int nx, int ny, int nz, void* dc_out, cudaStream_t s, int y_off = 0) {
 #define TPME_LINES(NN) \
-  case NN: return launch_lines<T, GT, NN, MODE, GV>(data, n_outer, n_inner, ls, d1, s1, s0, green, nx, ny, nz, dc_out, s);
+  case NN: return launch_lines<T, GT, NN, MODE, GV>(data, n_outer, n_inner, ls, d1, s1, s0, green, nx, ny, nz, dc_out, s, y_off);
   switch (n) {
     TPME_LINES(8) TPME_LINES(16) TPME_LINES(32) TPME_LINES(64) TPME_LINES(128) TPME_LINES(256) TPME_LINES(512)
   }
@@ -918,42 +919,60 @@ int green_variant(const GreenDev<GT>& g) {
   return g.p3m_nodes > 0 ? GV_TRI_P3M : GV_TRI;
 }
 
-// out = iFFT3(G * FFT3(in)), unnormalised; `hat` is (C, nx, ny, nz/2+1) complex scratch.
-// FAST = false compiles only the generic Green variant (used for float meshes with double G).
+// x pass fused with G on a (channels, nx, ny_local, nz/2+1) half-complex array holding the rows
+// y0 .. y0 + ny_local - 1 of the global mesh (ny_local == ny, y0 == 0: the whole mesh)
 template <typename T, typename GT, bool FAST>
-int filter_pow2(const void* in, void* out, void* hat, int channels, int nx, int ny, int nz,
-                const GreenDev<GT>& green_in, void* dc_out, cudaStream_t s) {
+int x_pass_green(void* hat, int channels, int nx, int ny, int nz, int y0, int ny_local,
+                 const GreenDev<GT>& green_in, void* dc_out, cudaStream_t s) {
   const int nzh = nz / 2 + 1;
-  const int64_t rows = (int64_t)channels * nx * ny;
   GreenDev<GT> green = green_in;
   const int gv = FAST ? green_variant(green) : (int)GV_GENERIC;
   // the fast variants evaluate amp * exp(-c k^2) / k^2; the p = 1 power law carries 1 / (c k^2)
   if (gv != GV_GENERIC && green.kind == 2) green.amplitude = green.amplitude / green.half_s2;
-  // (y, z) passes: fused per-plane kernel when the plane fits in shared memory
-  int prc = dispatch_plane<T>(ny, nz, true, in, hat, channels * nx, s);
-  if (prc > 0) return prc;
-  if (prc < 0) {
-    if (int rc = dispatch_rows<T>(nz, true, in, hat, rows, s)) return rc;
-    // y pass: outer = (c, x), line stride nzh
-    if (int rc = dispatch_lines<T, GT, 0, GV_GENERIC>(ny, hat, channels * nx, nzh, nzh, 1 << 30, 0,
-                                                      (int64_t)ny * nzh, green, nx, ny, nz, nullptr, s)) return rc;
-  }
-  // x pass fused with G: outer = (c, y), line stride ny * nzh
+  // outer = (c, y), line stride ny_local * nzh
   int rc = 0;
-#define TPME_XPASS(GV)                                                                           \
-  rc = dispatch_lines<T, GT, 2, GV>(nx, hat, channels * ny, nzh, (int64_t)ny * nzh, ny,          \
-                                    (int64_t)nx * ny * nzh, nzh, green, nx, ny, nz, dc_out, s)
+#define TPME_XPASS(GV)                                                                                   \
+  rc = dispatch_lines<T, GT, 2, GV>(nx, hat, channels * ny_local, nzh, (int64_t)ny_local * nzh, ny_local, \
+                                    (int64_t)nx * ny_local * nzh, nzh, green, nx, ny, nz, dc_out, s, y0)
   if (FAST && gv == GV_ORTHO) TPME_XPASS(GV_ORTHO);
   else if (FAST && gv == GV_TRI) TPME_XPASS(GV_TRI);
   else if (FAST && gv == GV_TRI_P3M) TPME_XPASS(GV_TRI_P3M);
   else TPME_XPASS(GV_GENERIC);
 #undef TPME_XPASS
-  if (rc) return rc;
-  prc = dispatch_plane<T>(ny, nz, false, hat, out, channels * nx, s);
+  return rc;
+}
+
+// (y, z) passes of `planes` (channel, x) planes: real (planes, ny, nz) -> half-complex
+// (planes, ny, nz/2+1) when `forward`, the reverse otherwise (the half-complex input is destroyed).
+// Fused per-plane kernel when the plane fits in shared memory, separate z / y passes otherwise.
+template <typename T, typename GT>
+int yz_passes(bool forward, void* real, void* hat, int planes, int ny, int nz, cudaStream_t s) {
+  const int nzh = nz / 2 + 1;
+  const int64_t rows = (int64_t)planes * ny;
+  GreenDev<GT> unused{};
+  if (forward) {
+    const int prc = dispatch_plane<T>(ny, nz, true, real, hat, planes, s);
+    if (prc >= 0) return prc;
+    if (int rc = dispatch_rows<T>(nz, true, real, hat, rows, s)) return rc;
+    // y pass: outer = (c, x), line stride nzh
+    return dispatch_lines<T, GT, 0, GV_GENERIC>(ny, hat, planes, nzh, nzh, 1 << 30, 0, (int64_t)ny * nzh,
+                                                unused, 0, ny, nz, nullptr, s);
+  }
+  const int prc = dispatch_plane<T>(ny, nz, false, hat, real, planes, s);
   if (prc >= 0) return prc;
-  if ((rc = dispatch_lines<T, GT, 1, GV_GENERIC>(ny, hat, channels * nx, nzh, nzh, 1 << 30, 0,
-                                                 (int64_t)ny * nzh, green, nx, ny, nz, nullptr, s))) return rc;
-  return dispatch_rows<T>(nz, false, hat, out, rows, s);
+  if (int rc = dispatch_lines<T, GT, 1, GV_GENERIC>(ny, hat, planes, nzh, nzh, 1 << 30, 0, (int64_t)ny * nzh,
+                                                    unused, 0, ny, nz, nullptr, s)) return rc;
+  return dispatch_rows<T>(nz, false, hat, real, rows, s);
+}
+
+// out = iFFT3(G * FFT3(in)), unnormalised; `hat` is (C, nx, ny, nz/2+1) complex scratch.
+// FAST = false compiles only the generic Green variant (used for float meshes with double G).
+template <typename T, typename GT, bool FAST>
+int filter_pow2(const void* in, void* out, void* hat, int channels, int nx, int ny, int nz,
+                const GreenDev<GT>& green, void* dc_out, cudaStream_t s) {
+  if (int rc = yz_passes<T, GT>(true, const_cast<void*>(in), hat, channels * nx, ny, nz, s)) return rc;
+  if (int rc = x_pass_green<T, GT, FAST>(hat, channels, nx, ny, nz, 0, ny, green, dc_out, s)) return rc;
+  return yz_passes<T, GT>(false, out, hat, channels * nx, ny, nz, s);
 }
 
 }  // namespace fft

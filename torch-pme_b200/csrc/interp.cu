@@ -68,6 +68,9 @@ __device__ __forceinline__ T pick(const T (&arr)[N], int k) {
 // (the contiguous mesh axis, so a warp-wide access touches runs of N consecutive mesh values per
 // (x, y) row) and loops over the N x N (a, b) rows.  Only G lanes repeat the per-point weight
 // evaluation.
+// marks a stencil plane that lies outside the local x slab (slab-decomposed meshes)
+constexpr unsigned kOutside = 0xFFFFFFFFu;
+
 template <int N> struct GroupSize {
   static constexpr int value = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : 8;
 };
@@ -78,7 +81,7 @@ template <int N> struct GroupSize {
 template <typename T, int METHOD, int N>
 __global__ void __launch_bounds__(256)
 spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, int64_t n_points,
-              int n_channels, Mat3<T> r2u, MeshDims<T> dims, T* __restrict__ mesh) {
+              int n_channels, Mat3<T> r2u, MeshDims<T> dims, int x0, int nxl, T* __restrict__ mesh) {
   constexpr int G = GroupSize<N>::value;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t point = tid / G;
@@ -91,13 +94,14 @@ spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, in
   point_stencil<T, METHOD, N, false>(positions + 3 * point, r2u, dims, first, w, dw);
   const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
   const unsigned plane = (unsigned)ny * nz;
-  const int64_t mesh_size = (int64_t)plane * nx;
+  const int64_t mesh_size = (int64_t)plane * nxl;   // the local slab holds x planes x0 .. x0 + nxl - 1
   unsigned xoff[N], yoff[N];
   {
     int ix = first[0], iy = first[1];
 #pragma unroll
     for (int a = 0; a < N; ++a) {
-      xoff[a] = (unsigned)ix * plane;
+      const unsigned lx = (unsigned)(ix - x0);
+      xoff[a] = lx < (unsigned)nxl ? lx * plane : kOutside;
       yoff[a] = (unsigned)iy * nz;
       ix = (ix + 1 >= nx) ? wrap_add(ix + 1, nx) : ix + 1;
       iy = (iy + 1 >= ny) ? wrap_add(iy + 1, ny) : iy + 1;
@@ -110,6 +114,7 @@ spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, in
     T* dst = mesh + ch * mesh_size + iz;
 #pragma unroll
     for (int a = 0; a < N; ++a) {
+      if (xoff[a] == kOutside) continue;
       const T qa = q * w[0][a];
 #pragma unroll
       for (int b = 0; b < N; ++b) red_add(dst + (xoff[a] + yoff[b]), qa * w[1][b]);
@@ -166,7 +171,7 @@ template <typename T, int METHOD, int N, int MODE>
 __global__ void __launch_bounds__(256, (N <= 4 && sizeof(T) == 4) ? 4 : 2)
 gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
               const T* __restrict__ coef, int64_t n_points, int n_channels, Mat3<T> r2u,
-              MeshDims<T> dims, T* __restrict__ values, T* __restrict__ dvalues,
+              MeshDims<T> dims, int x0, int nxl, T* __restrict__ values, T* __restrict__ dvalues,
               T* __restrict__ grad_positions, int accumulate, T* __restrict__ grad_r2u,
               PointEpilogue<T> epi) {
   constexpr int G = GroupSize<N>::value;
@@ -183,13 +188,14 @@ gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
   point_stencil<T, METHOD, N, DERIV>(positions + 3 * point, r2u, dims, first, w, dw);
   const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
   const unsigned plane = (unsigned)ny * nz;
-  const int64_t mesh_size = (int64_t)plane * nx;
+  const int64_t mesh_size = (int64_t)plane * nxl;   // the local slab holds x planes x0 .. x0 + nxl - 1
   unsigned xoff[N], yoff[N];
   {
     int ix = first[0], iy = first[1];
 #pragma unroll
     for (int a = 0; a < N; ++a) {
-      xoff[a] = (unsigned)ix * plane;
+      const unsigned lx = (unsigned)(ix - x0);
+      xoff[a] = lx < (unsigned)nxl ? lx * plane : kOutside;
       yoff[a] = (unsigned)iy * nz;
       ix = (ix + 1 >= nx) ? wrap_add(ix + 1, nx) : ix + 1;
       iy = (iy + 1 >= ny) ? wrap_add(iy + 1, ny) : iy + 1;
@@ -206,6 +212,7 @@ gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
     T s0 = T(0), s1 = T(0), s2 = T(0);
 #pragma unroll
     for (int a = 0; a < N; ++a) {
+      if (xoff[a] == kOutside) continue;
       T t0 = T(0), t1 = T(0);
 #pragma unroll
       for (int b = 0; b < N; ++b) {
@@ -298,22 +305,23 @@ static MeshDims<T> make_dims(int nx, int ny, int nz) {
 
 template <typename T, int METHOD, int N>
 int launch_spread(const void* positions, const void* weights, int64_t n_points, int n_channels,
-                  const double* r2u, int nx, int ny, int nz, void* mesh, cudaStream_t stream) {
+                  const double* r2u, int nx, int ny, int nz, int x0, int nxl, void* mesh,
+                  cudaStream_t stream) {
   const int64_t threads = n_points * GroupSize<N>::value;  // one lane per (point, z offset)
   const int block = 256;
   const int64_t grid = (threads + block - 1) / block;
   if (grid == 0) return 0;
   spread_kernel<T, METHOD, N><<<(unsigned)grid, block, 0, stream>>>(
       (const T*)positions, (const T*)weights, n_points, n_channels, load_mat3<T>(r2u),
-      make_dims<T>(nx, ny, nz), (T*)mesh);
+      make_dims<T>(nx, ny, nz), x0, nxl, (T*)mesh);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <typename T, int METHOD, int N, int MODE>
 int launch_gather(const void* mesh, const void* positions, const void* coef, int64_t n_points,
-                  int n_channels, const double* r2u, int nx, int ny, int nz, void* values,
-                  void* dvalues, void* grad_positions, int accumulate, void* grad_r2u,
+                  int n_channels, const double* r2u, int nx, int ny, int nz, int x0, int nxl,
+                  void* values, void* dvalues, void* grad_positions, int accumulate, void* grad_r2u,
                   const tpme_point_epilogue* epi_host, cudaStream_t stream) {
   constexpr int G = GroupSize<N>::value;
   PointEpilogue<T> epi;
@@ -334,7 +342,7 @@ int launch_gather(const void* mesh, const void* positions, const void* coef, int
   if (grid == 0) return 0;
   gather_kernel<T, METHOD, N, MODE><<<(unsigned)grid, block, 0, stream>>>(
       (const T*)mesh, (const T*)positions, (const T*)coef, n_points, n_channels,
-      load_mat3<T>(r2u), make_dims<T>(nx, ny, nz), (T*)values, (T*)dvalues, (T*)grad_positions,
+      load_mat3<T>(r2u), make_dims<T>(nx, ny, nz), x0, nxl, (T*)values, (T*)dvalues, (T*)grad_positions,
       accumulate, (T*)grad_r2u, epi);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
@@ -363,22 +371,23 @@ int launch_gather(const void* mesh, const void* positions, const void* coef, int
 
 template <typename T>
 int spread_dispatch(const void* positions, const void* weights, int64_t n_points, int n_channels,
-                    const double* r2u, int nx, int ny, int nz, int nodes, int method, void* mesh,
-                    cudaStream_t stream) {
+                    const double* r2u, int nx, int ny, int nz, int x0, int nxl, int nodes, int method,
+                    void* mesh, cudaStream_t stream) {
 #define CALL(M, N) \
-  launch_spread<T, M, N>(positions, weights, n_points, n_channels, r2u, nx, ny, nz, mesh, stream)
+  launch_spread<T, M, N>(positions, weights, n_points, n_channels, r2u, nx, ny, nz, x0, nxl, mesh, stream)
   TPME_DISPATCH_STENCIL(CALL)
 #undef CALL
 }
 
 template <typename T, int MODE>
 int gather_dispatch(const void* mesh, const void* positions, const void* coef, int64_t n_points,
-                    int n_channels, const double* r2u, int nx, int ny, int nz, int nodes,
-                    int method, void* values, void* dvalues, void* grad_positions, int accumulate,
-                    void* grad_r2u, const tpme_point_epilogue* epi, cudaStream_t stream) {
-#define CALL(M, N)                                                                              \
-  launch_gather<T, M, N, MODE>(mesh, positions, coef, n_points, n_channels, r2u, nx, ny, nz,   \
-                               values, dvalues, grad_positions, accumulate, grad_r2u, epi, stream)
+                    int n_channels, const double* r2u, int nx, int ny, int nz, int x0, int nxl,
+                    int nodes, int method, void* values, void* dvalues, void* grad_positions,
+                    int accumulate, void* grad_r2u, const tpme_point_epilogue* epi,
+                    cudaStream_t stream) {
+#define CALL(M, N)                                                                                 \
+  launch_gather<T, M, N, MODE>(mesh, positions, coef, n_points, n_channels, r2u, nx, ny, nz, x0,  \
+                               nxl, values, dvalues, grad_positions, accumulate, grad_r2u, epi, stream)
   TPME_DISPATCH_STENCIL(CALL)
 #undef CALL
 }
@@ -394,36 +403,52 @@ static int check_mesh_args(int dtype, int nx, int ny, int nz, int n_channels, in
 
 using namespace tpme;
 
+static int check_slab(int nx, int x0, int nxl) {
+  TPME_REQUIRE(x0 >= 0 && nxl > 0 && x0 + nxl <= nx, "slab [x0, x0 + nx_local) must lie inside [0, nx)");
+  return 0;
+}
+
+extern "C" int tpme_spread_slab(int dtype, const void* positions, const void* weights,
+                                int64_t n_points, int n_channels, const double* r2u_host, int nx,
+                                int ny, int nz, int x0, int nx_local, int nodes, int method,
+                                void* mesh, int accumulate, void* stream) {
+  if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
+  if (int rc = check_slab(nx, x0, nx_local)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t elem = dtype == 0 ? 4 : 8;
+  if (!accumulate)
+    TPME_CUDA_OK(cudaMemsetAsync(mesh, 0, elem * (size_t)n_channels * nx_local * ny * nz, s));
+  if (n_points == 0 || n_channels == 0) return 0;
+  if (dtype == 0)
+    return spread_dispatch<float>(positions, weights, n_points, n_channels, r2u_host, nx, ny, nz,
+                                  x0, nx_local, nodes, method, mesh, s);
+  return spread_dispatch<double>(positions, weights, n_points, n_channels, r2u_host, nx, ny, nz,
+                                 x0, nx_local, nodes, method, mesh, s);
+}
+
 extern "C" int tpme_spread(int dtype, const void* positions, const void* weights,
                            int64_t n_points, int n_channels, const double* r2u_host, int nx,
                            int ny, int nz, int nodes, int method, void* mesh, int accumulate,
                            void* stream) {
-  if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  const size_t elem = dtype == 0 ? 4 : 8;
-  if (!accumulate)
-    TPME_CUDA_OK(cudaMemsetAsync(mesh, 0, elem * (size_t)n_channels * nx * ny * nz, s));
-  if (n_points == 0 || n_channels == 0) return 0;
-  if (dtype == 0)
-    return spread_dispatch<float>(positions, weights, n_points, n_channels, r2u_host, nx, ny, nz,
-                                  nodes, method, mesh, s);
-  return spread_dispatch<double>(positions, weights, n_points, n_channels, r2u_host, nx, ny, nz,
-                                 nodes, method, mesh, s);
+  return tpme_spread_slab(dtype, positions, weights, n_points, n_channels, r2u_host, nx, ny, nz, 0,
+                          nx, nodes, method, mesh, accumulate, stream);
 }
 
-extern "C" int tpme_gather(int dtype, const void* mesh, const void* positions, int64_t n_points,
-                           int n_channels, const double* r2u_host, int nx, int ny, int nz,
-                           int nodes, int method, void* values, void* dvalues,
-                           const tpme_point_epilogue* epilogue, void* stream) {
+extern "C" int tpme_gather_slab(int dtype, const void* mesh, const void* positions,
+                                int64_t n_points, int n_channels, const double* r2u_host, int nx,
+                                int ny, int nz, int x0, int nx_local, int nodes, int method,
+                                void* values, void* dvalues, const tpme_point_epilogue* epilogue,
+                                void* stream) {
   if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
+  if (int rc = check_slab(nx, x0, nx_local)) return rc;
   TPME_REQUIRE(values != nullptr || dvalues != nullptr, "nothing to compute");
   if (n_points == 0 || n_channels == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const int mode = (values ? 1 : 0) | (dvalues ? 2 : 0);
 #define GO(T, MODE)                                                                          \
   return gather_dispatch<T, MODE>(mesh, positions, nullptr, n_points, n_channels, r2u_host,  \
-                                  nx, ny, nz, nodes, method, values, dvalues, nullptr, 0,    \
-                                  nullptr, epilogue, s)
+                                  nx, ny, nz, x0, nx_local, nodes, method, values, dvalues,  \
+                                  nullptr, 0, nullptr, epilogue, s)
   if (dtype == 0) {
     if (mode == 1) GO(float, 1);
     if (mode == 2) GO(float, 2);
@@ -435,13 +460,22 @@ extern "C" int tpme_gather(int dtype, const void* mesh, const void* positions, i
 #undef GO
 }
 
-extern "C" int tpme_gather_vjp(int dtype, const void* mesh, const void* positions,
-                               const void* coef, int64_t n_points, int n_channels,
-                               const double* r2u_host, int nx, int ny, int nz, int nodes,
-                               int method, void* grad_positions, void* values, int accumulate,
-                               void* grad_r2u, const tpme_point_epilogue* epilogue,
-                               void* stream) {
+extern "C" int tpme_gather(int dtype, const void* mesh, const void* positions, int64_t n_points,
+                           int n_channels, const double* r2u_host, int nx, int ny, int nz,
+                           int nodes, int method, void* values, void* dvalues,
+                           const tpme_point_epilogue* epilogue, void* stream) {
+  return tpme_gather_slab(dtype, mesh, positions, n_points, n_channels, r2u_host, nx, ny, nz, 0, nx,
+                          nodes, method, values, dvalues, epilogue, stream);
+}
+
+extern "C" int tpme_gather_vjp_slab(int dtype, const void* mesh, const void* positions,
+                                    const void* coef, int64_t n_points, int n_channels,
+                                    const double* r2u_host, int nx, int ny, int nz, int x0,
+                                    int nx_local, int nodes, int method, void* grad_positions,
+                                    void* values, int accumulate, void* grad_r2u,
+                                    const tpme_point_epilogue* epilogue, void* stream) {
   if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
+  if (int rc = check_slab(nx, x0, nx_local)) return rc;
   TPME_REQUIRE(grad_positions != nullptr && coef != nullptr, "grad_positions / coef missing");
   if (n_points == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
@@ -452,8 +486,8 @@ extern "C" int tpme_gather_vjp(int dtype, const void* mesh, const void* position
   }
 #define GO(T, MODE)                                                                           \
   return gather_dispatch<T, MODE>(mesh, positions, coef, n_points, n_channels, r2u_host, nx,  \
-                                  ny, nz, nodes, method, values, nullptr, grad_positions,     \
-                                  accumulate, grad_r2u, epilogue, s)
+                                  ny, nz, x0, nx_local, nodes, method, values, nullptr,       \
+                                  grad_positions, accumulate, grad_r2u, epilogue, s)
   if (dtype == 0) {
     if (values) GO(float, 5);
     GO(float, 4);
@@ -461,4 +495,15 @@ extern "C" int tpme_gather_vjp(int dtype, const void* mesh, const void* position
   if (values) GO(double, 5);
   GO(double, 4);
 #undef GO
+}
+
+extern "C" int tpme_gather_vjp(int dtype, const void* mesh, const void* positions,
+                               const void* coef, int64_t n_points, int n_channels,
+                               const double* r2u_host, int nx, int ny, int nz, int nodes,
+                               int method, void* grad_positions, void* values, int accumulate,
+                               void* grad_r2u, const tpme_point_epilogue* epilogue,
+                               void* stream) {
+  return tpme_gather_vjp_slab(dtype, mesh, positions, coef, n_points, n_channels, r2u_host, nx, ny,
+                              nz, 0, nx, nodes, method, grad_positions, values, accumulate, grad_r2u,
+                              epilogue, stream);
 }

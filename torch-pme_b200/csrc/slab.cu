@@ -1,0 +1,205 @@
+// Slab-decomposed reciprocal-space stage (one x slab of the real mesh per GPU):
+//
+//   (y,z) passes on the local x planes -> exchange (x slabs -> y slabs) -> x pass . G . inverse x
+//   pass on the local y rows -> exchange back -> inverse (y,z) passes
+//
+// (the single-GPU reference ops are lib/kspace_filter.py:169-187).
+// The exchange is a strided block copy whose destinations are either blocks of a local send
+// buffer (then NCCL all-to-all moves them) or the receive buffers of the peer GPUs mapped into
+// this process (NVLink peer stores: pack + transfer + unpack in one kernel), followed by a
+// device-side barrier over flags in peer memory.
+#include <cstring>
+
+#include "common.cuh"
+#include "green.cuh"
+#include "../../include/torchpme_b200.h"
+
+namespace tpme {
+
+int slab_yz_f32(bool, void*, void*, int, int, int, cudaStream_t);
+int slab_yz_f64(bool, void*, void*, int, int, int, cudaStream_t);
+int slab_x_f32(void*, int, int, int, int, int, int, const GreenDev<float>&, void*, cudaStream_t);
+int slab_x_f64(void*, int, int, int, int, int, int, const GreenDev<double>&, void*, cudaStream_t);
+int slab_x_f32d(void*, int, int, int, int, int, int, const GreenDev<double>&, void*, cudaStream_t);
+
+static bool pow2_dim(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
+
+// ---------------------------------------------------------------------------------------
+// exchange copy: for every (c, p, a) copy `run` contiguous 16-byte (or 8-byte) words
+//   dst[p][c * dst_c + a * dst_a + i] = src[c * src_c + p * src_p + a * src_a + i]
+// One CTA row per (c, p, a) chunk, grid.y splits long runs.
+// ---------------------------------------------------------------------------------------
+struct PeerPointers { void* p[TPME_MAX_RANKS]; };
+
+template <typename W>
+__global__ void __launch_bounds__(256)
+exchange_copy_kernel(const W* __restrict__ src, PeerPointers dst, int n_p, int n_a, int64_t run,
+                     int64_t src_c, int64_t src_p, int64_t src_a, int64_t dst_c, int64_t dst_a) {
+  const int chunk = blockIdx.x;
+  const int a = chunk % n_a;
+  const int p = (chunk / n_a) % n_p;
+  const int c = chunk / (n_a * n_p);
+  const W* s = src + c * src_c + p * src_p + a * src_a;
+  W* d = reinterpret_cast<W*>(dst.p[p]) + c * dst_c + a * dst_a;
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < run;
+       i += (int64_t)gridDim.y * blockDim.x)
+    d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// device-side barrier over flags in peer memory.  Every rank owns `flags[n_ranks]` (uint32,
+// zero-initialised) plus a local epoch counter; arrival adds 1 to flags[rank] of every peer, the
+// wait spins until all of its own flags reached the epoch.  No kernel argument changes between
+// calls, so the barrier can be replayed from a CUDA graph.  A rank that waits longer than
+// `timeout_ns` raises `*error` instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------
+__global__ void peer_barrier_kernel(PeerPointers flags, int n_ranks, int rank, unsigned* epoch,
+                                    unsigned long long timeout_ns, int* error) {
+  __shared__ unsigned target;
+  if (threadIdx.x == 0) {
+    target = *epoch + 1;
+    *epoch = target;
+  }
+  __syncthreads();
+  const int peer = threadIdx.x;
+  if (peer < n_ranks) {
+    __threadfence_system();   // order this GPU's earlier peer stores before the arrival
+    unsigned* remote = reinterpret_cast<unsigned*>(flags.p[peer]) + rank;
+    atomicAdd_system(remote, 1u);
+    volatile unsigned* mine = reinterpret_cast<unsigned*>(flags.p[rank]) + peer;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int)(*mine - target) < 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) {
+        atomicExch(error, 1 + peer);
+        break;
+      }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+}
+
+}  // namespace tpme
+
+using namespace tpme;
+
+extern "C" int tpme_slab_fft_yz(int dtype, int forward, void* real_mesh, void* mesh_hat,
+                                int n_planes, int ny, int nz, void* stream) {
+  TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 or 1");
+  TPME_REQUIRE(pow2_dim(ny) && pow2_dim(nz),
+               "the slab-decomposed FFT needs power-of-two mesh dimensions in 8..512");
+  if (n_planes <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  return dtype == 0 ? slab_yz_f32(forward != 0, real_mesh, mesh_hat, n_planes, ny, nz, s)
+                    : slab_yz_f64(forward != 0, real_mesh, mesh_hat, n_planes, ny, nz, s);
+}
+
+extern "C" int tpme_slab_fft_x_green(int dtype, void* mesh_hat_t, int n_channels, int nx, int ny,
+                                     int nz, int y0, int ny_local, const tpme_green* green,
+                                     void* stream) {
+  TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 or 1");
+  TPME_REQUIRE(pow2_dim(nx), "the slab-decomposed FFT needs power-of-two mesh dimensions in 8..512");
+  TPME_REQUIRE(y0 >= 0 && ny_local > 0 && y0 + ny_local <= ny, "y slab must lie inside [0, ny)");
+  if (int rc = check_green(green)) return rc;
+  if (n_channels <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == 1)
+    return slab_x_f64(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<double>(green), nullptr, s);
+  if (needs_double_math(green))
+    return slab_x_f32d(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<double>(green), nullptr, s);
+  return slab_x_f32(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<float>(green), nullptr, s);
+}
+
+extern "C" int tpme_slab_exchange_copy(int elem_bytes, const void* src, void* const* dst_host,
+                                       int n_c, int n_p, int n_a, int64_t run, int64_t src_c,
+                                       int64_t src_p, int64_t src_a, int64_t dst_c, int64_t dst_a,
+                                       void* stream) {
+  TPME_REQUIRE(elem_bytes == 8 || elem_bytes == 16, "elements are complex float (8) or complex double (16)");
+  TPME_REQUIRE(n_p > 0 && n_p <= TPME_MAX_RANKS, "number of destinations out of range");
+  TPME_REQUIRE(n_c >= 0 && n_a >= 0 && run >= 0, "negative sizes");
+  if (n_c == 0 || n_a == 0 || run == 0) return 0;
+  PeerPointers dst;
+  memset(&dst, 0, sizeof(dst));
+  for (int p = 0; p < n_p; ++p) dst.p[p] = dst_host[p];
+  const int64_t chunks = (int64_t)n_c * n_p * n_a;
+  TPME_REQUIRE(chunks < (1ll << 31), "too many exchange chunks");
+  cudaStream_t s = (cudaStream_t)stream;
+  // 16-byte words when everything is 16-byte aligned, else 8-byte words
+  bool wide = elem_bytes == 16;
+  if (!wide) {
+    wide = (run % 2 == 0) && (src_c % 2 == 0) && (src_p % 2 == 0) && (src_a % 2 == 0) &&
+           (dst_c % 2 == 0) && (dst_a % 2 == 0) && ((uintptr_t)src % 16 == 0);
+    for (int p = 0; p < n_p && wide; ++p) wide = ((uintptr_t)dst.p[p] % 16 == 0);
+  }
+  const int64_t words = (wide && elem_bytes == 8) ? run / 2 : run;
+  const int div = (wide && elem_bytes == 8) ? 2 : 1;
+  // enough CTAs to fill the machine (~8 per SM), at most one CTA per 256 words of a chunk
+  int64_t split = (8ll * num_sms() + chunks - 1) / chunks;
+  const int64_t max_split = (words + 255) / 256;
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  if (split > 65535) split = 65535;
+  dim3 grid((unsigned)chunks, (unsigned)split);
+  if (wide)
+    exchange_copy_kernel<uint4><<<grid, 256, 0, s>>>((const uint4*)src, dst, n_p, n_a, words, src_c / div,
+                                                     src_p / div, src_a / div, dst_c / div, dst_a / div);
+  else
+    exchange_copy_kernel<uint2><<<grid, 256, 0, s>>>((const uint2*)src, dst, n_p, n_a, words, src_c, src_p,
+                                                     src_a, dst_c, dst_a);
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- peer memory ------------------------------------------------------------------------
+extern "C" int tpme_peer_buffer_create(int64_t bytes, void** dev_ptr, unsigned char* handle_out) {
+  TPME_REQUIRE(bytes > 0 && dev_ptr != nullptr && handle_out != nullptr, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == TPME_IPC_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  TPME_CUDA_OK(cudaMalloc(&p, (size_t)bytes));
+  TPME_CUDA_OK(cudaMemset(p, 0, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t err = cudaIpcGetMemHandle(&h, p);
+  if (err != cudaSuccess) {
+    cudaFree(p);
+    set_last_error("cudaIpcGetMemHandle", cudaGetErrorString(err));
+    return 100 + (int)err;
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return 0;
+}
+
+extern "C" int tpme_peer_buffer_open(const unsigned char* handle, void** dev_ptr) {
+  TPME_REQUIRE(handle != nullptr && dev_ptr != nullptr, "bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  TPME_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int tpme_peer_buffer_close(void* dev_ptr) {
+  if (dev_ptr) TPME_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
+extern "C" int tpme_peer_buffer_destroy(void* dev_ptr) {
+  if (dev_ptr) TPME_CUDA_OK(cudaFree(dev_ptr));
+  return 0;
+}
+
+extern "C" int tpme_peer_barrier(void* const* flags_host, int n_ranks, int rank, void* epoch,
+                                 double timeout_seconds, void* error_flag, void* stream) {
+  TPME_REQUIRE(n_ranks > 0 && n_ranks <= TPME_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank layout");
+  TPME_REQUIRE(flags_host != nullptr && epoch != nullptr && error_flag != nullptr, "null pointers");
+  PeerPointers flags;
+  memset(&flags, 0, sizeof(flags));
+  for (int p = 0; p < n_ranks; ++p) flags.p[p] = flags_host[p];
+  const unsigned long long ns = (unsigned long long)(timeout_seconds * 1e9);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n_ranks, rank, (unsigned*)epoch, ns,
+                                                          (int*)error_flag);
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
+}

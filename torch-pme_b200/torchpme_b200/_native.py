@@ -82,6 +82,20 @@ SIGNATURES = {
                      ctypes.POINTER(_PointEpilogue), _vp], _i),
     "tpme_gather_vjp": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp,
                          ctypes.POINTER(_PointEpilogue), _vp], _i),
+    "tpme_spread_slab": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
+    "tpme_gather_slab": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp,
+                          ctypes.POINTER(_PointEpilogue), _vp], _i),
+    "tpme_gather_vjp_slab": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i,
+                              _vp, ctypes.POINTER(_PointEpilogue), _vp], _i),
+    "tpme_slab_fft_yz": ([_i, _i, _vp, _vp, _i, _i, _i, _vp], _i),
+    "tpme_slab_fft_x_green": ([_i, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
+    "tpme_slab_exchange_copy": ([_i, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
+                                 _i64, _vp], _i),
+    "tpme_peer_buffer_create": ([_i64, ctypes.POINTER(_vp), ctypes.c_char_p], _i),
+    "tpme_peer_buffer_open": ([ctypes.c_char_p, ctypes.POINTER(_vp)], _i),
+    "tpme_peer_buffer_close": ([_vp], _i),
+    "tpme_peer_buffer_destroy": ([_vp], _i),
+    "tpme_peer_barrier": ([ctypes.POINTER(_vp), _i, _i, _vp, ctypes.c_double, _vp, _vp], _i),
     "tpme_fft_plan_create": ([ctypes.POINTER(_vp), _i, _i, _i, _i, _i], _i),
     "tpme_fft_plan_destroy": ([_vp], _i),
     "tpme_fft_plan_uses_own_fft": ([_vp], _i),
@@ -184,16 +198,19 @@ def _count(n=1):
 # --------------------------------------------------------------------------------------
 # mesh interpolation
 # --------------------------------------------------------------------------------------
-def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None):
+def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=None):
+    """`slab` = (x0, nx_local): spread into the local x slab (C, nx_local, ny, nz) only"""
     lib = load()
     n, c = weights.shape
     nx, ny, nz = ns
+    x0, nxl = (0, nx) if slab is None else slab
     if out is None:
-        out = torch.empty((c, nx, ny, nz), dtype=positions.dtype, device=positions.device)
+        out = torch.empty((c, nxl, ny, nz), dtype=positions.dtype, device=positions.device)
     with _on(positions, "positions"):
-        _check(lib.tpme_spread(_dtype_id(positions), _dev(positions, "positions"),
-                               _dev(weights, "particle_weights"), n, c, _mat9(r2u), nx, ny, nz,
-                               nodes, method, _dev(out, "mesh"), 0, _stream()), "tpme_spread")
+        _check(lib.tpme_spread_slab(_dtype_id(positions), _dev(positions, "positions"),
+                                    _dev(weights, "particle_weights"), n, c, _mat9(r2u), nx, ny, nz,
+                                    x0, nxl, nodes, method, _dev(out, "mesh"), 0, _stream()),
+               "tpme_spread")
     _count()
     return out
 
@@ -210,21 +227,33 @@ def make_epilogue(add_coef, dc, scale, self_half, background, coef2=None, dvalue
     return e
 
 
+def _slab_of(mesh, slab):
+    """(c, nx, ny, nz, x0, nx_local) of a full mesh or of a local slab `slab` = (x0, nx_global)"""
+    c, nxl, ny, nz = mesh.shape
+    if slab is None:
+        return c, nxl, ny, nz, 0, nxl
+    x0, nx = slab
+    return c, nx, ny, nz, x0, nxl
+
+
 def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want_grad=False,
-           values_out=None, epilogue: _PointEpilogue | None = None):
-    """plain gather, or (with `epilogue` and `values_out`) the fused accumulate form"""
+           values_out=None, epilogue: _PointEpilogue | None = None, slab=None):
+    """
+    plain gather, or (with `epilogue` and `values_out`) the fused accumulate form.
+    `slab` = (x0, nx_global): `mesh` is the local x slab and the results are partial sums.
+    """
     lib = load()
-    c, nx, ny, nz = mesh.shape
+    c, nx, ny, nz, x0, nxl = _slab_of(mesh, slab)
     n = positions.shape[0]
     values = values_out
     if values is None and want_values:
         values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device)
     dvalues = torch.empty((n, c, 3), dtype=mesh.dtype, device=mesh.device) if want_grad else None
     with _on(mesh, "mesh"):
-        _check(lib.tpme_gather(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"), n,
-                               c, _mat9(r2u), nx, ny, nz, nodes, method, _dev(values, "values"),
-                               _dev(dvalues, "dvalues"),
-                               ctypes.byref(epilogue) if epilogue is not None else None, _stream()),
+        _check(lib.tpme_gather_slab(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"), n,
+                                    c, _mat9(r2u), nx, ny, nz, x0, nxl, nodes, method,
+                                    _dev(values, "values"), _dev(dvalues, "dvalues"),
+                                    ctypes.byref(epilogue) if epilogue is not None else None, _stream()),
                "tpme_gather")
     _count()
     return values, dvalues
@@ -232,10 +261,10 @@ def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want
 
 def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positions=None,
                want_values=False, want_grad_r2u=False, values_out=None,
-               epilogue: _PointEpilogue | None = None):
-    """returns (grad_positions, values | None, grad_r2u (3,3) | None)"""
+               epilogue: _PointEpilogue | None = None, slab=None):
+    """returns (grad_positions, values | None, grad_r2u (3,3) | None); `slab` as in :func:`gather`"""
     lib = load()
-    c, nx, ny, nz = mesh.shape
+    c, nx, ny, nz, x0, nxl = _slab_of(mesh, slab)
     n = positions.shape[0]
     accumulate = grad_positions is not None
     if grad_positions is None:
@@ -245,12 +274,12 @@ def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positio
         values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device)
     grad_r2u = torch.zeros((3, 3), dtype=mesh.dtype, device=mesh.device) if want_grad_r2u else None
     with _on(mesh, "mesh"):
-        _check(lib.tpme_gather_vjp(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"),
-                                   _dev(coef, "coef"), n, c, _mat9(r2u), nx, ny, nz, nodes, method,
-                                   _dev(grad_positions, "grad_positions"), _dev(values, "values"),
-                                   int(accumulate), _dev(grad_r2u, "grad_r2u"),
-                                   ctypes.byref(epilogue) if epilogue is not None else None,
-                                   _stream()), "tpme_gather_vjp")
+        _check(lib.tpme_gather_vjp_slab(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"),
+                                        _dev(coef, "coef"), n, c, _mat9(r2u), nx, ny, nz, x0, nxl, nodes,
+                                        method, _dev(grad_positions, "grad_positions"),
+                                        _dev(values, "values"), int(accumulate), _dev(grad_r2u, "grad_r2u"),
+                                        ctypes.byref(epilogue) if epilogue is not None else None,
+                                        _stream()), "tpme_gather_vjp")
     _count()
     return grad_positions, values, grad_r2u
 
@@ -367,6 +396,122 @@ def green_table_vjp(x_hat, y_hat, ns, scale: float):
                "tpme_green_table_vjp")
     _count()
     return out
+
+
+# --------------------------------------------------------------------------------------
+# slab-decomposed reciprocal space (multi-GPU)
+# --------------------------------------------------------------------------------------
+MAX_RANKS = 16
+IPC_HANDLE_BYTES = 64
+
+
+def slab_fft_yz(forward: bool, real_mesh, mesh_hat):
+    """(y,z) passes of the local planes: real (C, nxl, ny, nz) <-> half-complex (C, nxl, ny, nz/2+1, 2)"""
+    lib = load()
+    c, nxl, ny, nz = real_mesh.shape
+    with _on(real_mesh, "mesh"):
+        _check(lib.tpme_slab_fft_yz(_dtype_id(real_mesh), int(forward), _dev(real_mesh, "mesh"),
+                                    _dev(mesh_hat, "mesh_hat"), c * nxl, ny, nz, _stream()), "tpme_slab_fft_yz")
+    # fused (y,z) plane kernel: 1 launch; otherwise rows + lines: 2
+    _count(1 if (ny <= 128 and nz <= 128) else 2)
+
+
+def slab_fft_x_green(mesh_hat_t, ns, y0: int, green: _Green):
+    """in place on (C, nx, ny_local, nz/2+1, 2): x transform, multiply by G, inverse x transform"""
+    lib = load()
+    nx, ny, nz = ns
+    c, nx_, nyl, nzh, _ = mesh_hat_t.shape
+    assert nx_ == nx and nzh == nz // 2 + 1
+    with _on(mesh_hat_t, "mesh_hat"):
+        _check(lib.tpme_slab_fft_x_green(_dtype_id(mesh_hat_t), _dev(mesh_hat_t, "mesh_hat"), c, nx, ny, nz,
+                                         y0, nyl, ctypes.byref(green), _stream()), "tpme_slab_fft_x_green")
+    _count()
+
+
+def slab_exchange_copy(src, dst_ptrs, n_c, n_p, n_a, run, src_strides, dst_strides):
+    """
+    dst[p][c * dst_c + a * dst_a + i] = src[c * src_c + p * src_p + a * src_a + i] in complex
+    elements; `dst_ptrs` are raw device addresses (local blocks or mapped peer buffers).
+    """
+    lib = load()
+    elem = 8 if src.dtype == torch.float32 else 16
+    arr = (_vp * n_p)(*[int(p) for p in dst_ptrs])
+    with _on(src, "src"):
+        _check(lib.tpme_slab_exchange_copy(elem, _dev(src, "src"), arr, n_c, n_p, n_a, run,
+                                           src_strides[0], src_strides[1], src_strides[2],
+                                           dst_strides[0], dst_strides[1], _stream()),
+               "tpme_slab_exchange_copy")
+    _count()
+
+
+class PeerBuffer:
+    """cudaMalloc'ed exchange buffer with a CUDA IPC handle (not managed by torch's allocator)"""
+
+    def __init__(self, n_bytes: int, device):
+        lib = load()
+        self.device = torch.device(device)
+        self.n_bytes = int(n_bytes)
+        ptr = _vp()
+        handle = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            _check(lib.tpme_peer_buffer_create(self.n_bytes, ctypes.byref(ptr), handle), "tpme_peer_buffer_create")
+        self.ptr = int(ptr.value)
+        self.handle = handle.raw
+        self._opened = []
+
+    def open_peer(self, handle: bytes) -> int:
+        lib = load()
+        ptr = _vp()
+        with torch.cuda.device(self.device):
+            _check(lib.tpme_peer_buffer_open(handle, ctypes.byref(ptr)), "tpme_peer_buffer_open")
+        self._opened.append(int(ptr.value))
+        return int(ptr.value)
+
+    def as_tensor(self, offset_bytes: int, shape, dtype) -> torch.Tensor:
+        """torch view of a region of the buffer (through the CUDA array interface)"""
+        n = 1
+        for v in shape:
+            n *= int(v)
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        assert offset_bytes + n * itemsize <= self.n_bytes
+
+        class _Region:
+            pass
+
+        region = _Region()
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        region.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr,
+                                           "data": (self.ptr + offset_bytes, False), "version": 2}
+        region._owner = self
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(region, device=self.device)
+
+    def close(self):
+        if _lib is None:
+            return
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                _lib.tpme_peer_buffer_close(_vp(p))
+            self._opened = []
+            if self.ptr:
+                _lib.tpme_peer_buffer_destroy(_vp(self.ptr))
+                self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def peer_barrier(flag_ptrs, rank: int, epoch, error_flag, timeout_seconds: float = 5.0):
+    lib = load()
+    n = len(flag_ptrs)
+    arr = (_vp * n)(*[int(p) for p in flag_ptrs])
+    with _on(epoch, "epoch"):
+        _check(lib.tpme_peer_barrier(arr, n, rank, _dev(epoch, "epoch"), float(timeout_seconds),
+                                     _dev(error_flag, "error_flag"), _stream()), "tpme_peer_barrier")
+    _count()
 
 
 # --------------------------------------------------------------------------------------

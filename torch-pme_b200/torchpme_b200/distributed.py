@@ -1,0 +1,418 @@
+"""
+Slab-decomposed PME / P3M across the GPUs of one node.
+
+One process per GPU (``torch.distributed``).  Every rank passes the *same* replicated
+``charges / cell / positions`` (16 B per atom) and the same neighbor list to
+``forward`` -- the reference call signature is unchanged -- and gets the same full ``(N, C)``
+potentials back.  Inside:
+
+* the mesh is cut into x slabs, rank ``g`` owns the planes ``[g nx/W, (g+1) nx/W)``;
+* **spread**: every rank scans all atoms and keeps only the stencil planes that fall into its
+  slab (``tpme_spread_slab``) -- no halo, no reduction;
+* **FFT . G . iFFT**: local (y,z) passes, exchange x slabs -> y slabs, x pass fused with the
+  Green's function on the local y rows, exchange back, inverse (y,z) passes.  The exchange is
+  either NCCL ``all_to_all_single`` around a packing copy kernel (``transport="nccl"``) or a
+  single copy kernel that stores straight into the peers' receive buffers over NVLink
+  followed by a device-side flag barrier (``transport="p2p"``: pack + transfer + unpack in one
+  kernel, no library call);
+* **gather**: partial sums over the local planes (``tpme_gather_slab``); they are summed over
+  the ranks by the same all-reduce that combines the real-space pair sum, whose pair list is
+  cut into ``W`` contiguous chunks;
+* backward mirrors this (the filter is self-adjoint) and ends with one all-reduce of the
+  ``(N, 3 + C)`` position / charge gradients.  The gradient w.r.t. ``neighbor_distances`` is
+  returned for the rank's own pair chunk (zeros elsewhere): summing it over ranks -- like any
+  data-parallel gradient -- gives the full one.
+
+Collectives per step (forward + backward): 4 exchanges of the half-complex mesh
+(``C nx ny (nz/2+1)`` complex numbers / W per rank each) and 2 all-reduces.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch.autograd.function import once_differentiable
+
+from . import _native
+from ._checks import validate_parameters
+from .calculators import P3MCalculator, PMECalculator, _side_stream
+from .mesh import geometry_of
+
+
+class SlabLayout:
+    """Host-side partition of an ``(nx, ny, nz)`` mesh and of a pair list over ``world`` ranks."""
+
+    def __init__(self, ns, world: int, rank: int):
+        nx, ny, nz = (int(v) for v in ns)
+        if world < 1 or not 0 <= rank < world:
+            raise ValueError(f"invalid rank {rank} for world size {world}")
+        if world > _native.MAX_RANKS:
+            raise ValueError(f"at most {_native.MAX_RANKS} ranks are supported, got {world}")
+        if nx % world or ny % world:
+            raise ValueError(
+                f"mesh {nx} x {ny} x {nz} cannot be cut into {world} x slabs and {world} y slabs; "
+                "the world size has to divide nx and ny"
+            )
+        self.ns, self.world, self.rank = (nx, ny, nz), world, rank
+        self.nxl, self.nyl, self.nzh = nx // world, ny // world, nz // 2 + 1
+        self.x0, self.y0 = rank * self.nxl, rank * self.nyl
+        #: complex elements of one exchanged block (one rank's x planes x one rank's y rows)
+        self.block = self.nxl * self.nyl * self.nzh
+
+    def pair_range(self, n_pairs: int):
+        """contiguous chunk of the pair list owned by this rank"""
+        per = -(-n_pairs // self.world)
+        lo = min(self.rank * per, n_pairs)
+        return lo, min(lo + per, n_pairs)
+
+
+def _ptr(t: torch.Tensor, offset_elems: int = 0) -> int:
+    return t.data_ptr() + offset_elems * t.element_size()
+
+
+class NcclExchange:
+    """x slabs <-> y slabs through ``all_to_all_single`` with packing kernels on both sides."""
+
+    name = "nccl"
+
+    def __init__(self, layout: SlabLayout, channels: int, dtype, device, group, ops):
+        self.layout, self.c, self.group, self.ops = layout, channels, group, ops
+        w, blk = layout.world, layout.block
+        shape = (w * channels * blk, 2)
+        self.buf_a = torch.empty(shape, dtype=dtype, device=device)
+        self.buf_b = torch.empty(shape, dtype=dtype, device=device)
+        nx, ny, _ = layout.ns
+        self.hat = torch.empty((channels, layout.nxl, ny, layout.nzh, 2), dtype=dtype, device=device)
+        self.hat_t = torch.empty((channels, nx, layout.nyl, layout.nzh, 2), dtype=dtype, device=device)
+
+    def x_to_y(self):
+        """self.hat (C, nxl, ny, nzh) -> self.hat_t (C, nx, nyl, nzh) of every rank"""
+        lay, c, ops = self.layout, self.c, self.ops
+        w, blk, run = lay.world, lay.block, lay.nyl * lay.nzh
+        ny = lay.ns[1]
+        # pack: block p = hat[:, :, p nyl:(p+1) nyl, :] as (C, nxl, nyl, nzh)
+        ops.slab_exchange_copy(self.hat, [_ptr(self.buf_a, 2 * p * c * blk) for p in range(w)],
+                               c, w, lay.nxl, run, (lay.nxl * ny * lay.nzh, run, ny * lay.nzh), (blk, run))
+        recv = self.hat_t.view(-1, 2) if c == 1 else self.buf_b
+        dist.all_to_all_single(recv, self.buf_a, group=self.group)
+        if c > 1:
+            # (W, C, blk) -> (C, W, blk)
+            ops.slab_exchange_copy(self.buf_b, [_ptr(self.hat_t, 2 * p * blk) for p in range(w)],
+                                   c, w, 1, blk, (blk, c * blk, 0), (w * blk, 0))
+        return self.hat_t
+
+    def y_to_x(self):
+        """self.hat_t (C, nx, nyl, nzh) -> self.hat (C, nxl, ny, nzh) of every rank"""
+        lay, c, ops = self.layout, self.c, self.ops
+        w, blk, run = lay.world, lay.block, lay.nyl * lay.nzh
+        ny = lay.ns[1]
+        if c == 1:
+            send = self.hat_t.view(-1, 2)
+        else:
+            send = self.buf_a
+            ops.slab_exchange_copy(self.hat_t, [_ptr(self.buf_a, 2 * p * c * blk) for p in range(w)],
+                                   c, w, 1, blk, (w * blk, blk, 0), (blk, 0))
+        dist.all_to_all_single(self.buf_b, send, group=self.group)
+        # block from rank p holds the y rows of p: (W, C, nxl, nyl, nzh) -> (C, nxl, W, nyl, nzh)
+        ops.slab_exchange_copy(self.buf_b, [_ptr(self.hat, 2 * p * run) for p in range(w)],
+                               c, w, lay.nxl, run, (blk, c * blk, run), (lay.nxl * ny * lay.nzh, ny * lay.nzh))
+        return self.hat
+
+
+class PeerExchange:
+    """
+    x slabs <-> y slabs by storing straight into the peers' buffers over NVLink: one copy kernel
+    packs, transfers and unpacks; a flag barrier in peer memory orders it (CUDA IPC, one node).
+    """
+
+    name = "p2p"
+    _FLAG_BYTES = 256
+
+    def __init__(self, layout: SlabLayout, channels: int, dtype, device, group, ops=None):
+        if device.type != "cuda":
+            raise ValueError("the peer-memory exchange needs CUDA devices")
+        self.layout, self.c, self.group, self.ops = layout, channels, group, ops or _native
+        w = layout.world
+        nx, ny, _ = layout.ns
+        esize = 8 if dtype == torch.float32 else 16
+        half = channels * layout.nxl * ny * layout.nzh * esize   # == C * nx * nyl * nzh * esize
+        half = (half + 255) // 256 * 256
+        self._off_x, self._off_t = self._FLAG_BYTES, self._FLAG_BYTES + half
+        self.buffer = _native.PeerBuffer(self._FLAG_BYTES + 2 * half, device)
+        # exchange the IPC handles and map the peers' buffers
+        mine = torch.tensor(list(self.buffer.handle), dtype=torch.uint8, device=device)
+        handles = [torch.empty_like(mine) for _ in range(w)]
+        dist.all_gather(handles, mine, group=group)
+        self.peer_base = []
+        for p in range(w):
+            if p == layout.rank:
+                self.peer_base.append(self.buffer.ptr)
+            else:
+                self.peer_base.append(self.buffer.open_peer(bytes(handles[p].cpu().tolist())))
+        self.esize = esize
+        self.hat = self.buffer.as_tensor(self._off_x, (channels, layout.nxl, ny, layout.nzh, 2), dtype)
+        self.hat_t = self.buffer.as_tensor(self._off_t, (channels, nx, layout.nyl, layout.nzh, 2), dtype)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier(group=group)   # every rank has mapped every buffer before the first store
+
+    def _barrier(self):
+        _native.peer_barrier(self.peer_base, self.layout.rank, self.epoch, self.error)
+
+    def check(self):
+        """host-side check of the barrier time-out flag (a device->host read)"""
+        code = int(self.error.item())
+        if code:
+            raise RuntimeError(f"peer barrier timed out waiting for rank {code - 1}")
+
+    def x_to_y(self):
+        lay, c = self.layout, self.c
+        w, blk, run = lay.world, lay.block, lay.nyl * lay.nzh
+        ny = lay.ns[1]
+        # my x planes go to rows [rank nxl, (rank+1) nxl) of every peer's (C, nx, nyl, nzh) array
+        dst = [self.peer_base[p] + self._off_t + lay.rank * blk * self.esize for p in range(w)]
+        self.ops.slab_exchange_copy(self.hat, dst, c, w, lay.nxl, run,
+                                    (lay.nxl * ny * lay.nzh, run, ny * lay.nzh), (w * blk, run))
+        self._barrier()
+        return self.hat_t
+
+    def y_to_x(self):
+        lay, c = self.layout, self.c
+        w, blk, run = lay.world, lay.block, lay.nyl * lay.nzh
+        ny = lay.ns[1]
+        # my y rows go to rows [rank nyl, (rank+1) nyl) of every peer's (C, nxl, ny, nzh) array
+        dst = [self.peer_base[p] + self._off_x + lay.rank * run * self.esize for p in range(w)]
+        self.ops.slab_exchange_copy(self.hat_t, dst, c, w, lay.nxl, run,
+                                    (w * blk, blk, run), (lay.nxl * ny * lay.nzh, ny * lay.nzh))
+        self._barrier()
+        return self.hat
+
+
+class SlabFilter:
+    """``irfft3(G * rfft3(.))`` of a mesh distributed as x slabs (buffers reused across calls)."""
+
+    def __init__(self, layout: SlabLayout, channels: int, dtype, device, group, transport="nccl",
+                 ops=None):
+        self.layout, self.ops = layout, ops or _native
+        if transport == "p2p":
+            self.exchange = PeerExchange(layout, channels, dtype, device, group, self.ops)
+        elif transport == "nccl":
+            self.exchange = NcclExchange(layout, channels, dtype, device, group, self.ops)
+        else:
+            raise ValueError(f"unknown transport '{transport}' (choose 'nccl' or 'p2p')")
+
+    def apply(self, rho_local: torch.Tensor, green) -> torch.Tensor:
+        """``rho_local`` (C, nxl, ny, nz) -> filtered slab of the same shape"""
+        ex, lay, ops = self.exchange, self.layout, self.ops
+        ops.slab_fft_yz(True, rho_local, ex.hat)
+        hat_t = ex.x_to_y()
+        ops.slab_fft_x_green(hat_t, lay.ns, lay.y0, green)
+        hat = ex.y_to_x()
+        out = torch.empty_like(rho_local)
+        ops.slab_fft_yz(False, out, hat)
+        return out
+
+
+class _SlabStepConfig:
+    __slots__ = ("r2u", "ns", "nodes", "method", "green_args", "pair_pot", "full_list", "half_ivolume",
+                 "self_half", "background_ivolume", "layout", "filter", "group", "ops", "shard_pairs")
+
+
+class _SlabMeshPotential(torch.autograd.Function):
+    """
+    Distributed counterpart of ``calculators._FusedMeshPotential``: one autograd node per
+    calculator forward; see the module docstring for the data flow.
+    """
+
+    @staticmethod
+    def forward(ctx, charges, positions, distances, neighbor_indices, mask_u8, cfg):
+        ops, lay = cfg.ops, cfg.layout
+        q = charges.detach().contiguous()
+        pos = positions.detach().contiguous()
+        need_pos = ctx.needs_input_grad[1]
+        n_pairs = neighbor_indices.shape[0]
+        lo, hi = lay.pair_range(n_pairs) if cfg.shard_pairs else (0, n_pairs)
+        idx = neighbor_indices[lo:hi].contiguous()
+        d = distances.detach()[lo:hi].contiguous()
+        mask = None if mask_u8 is None else mask_u8[lo:hi].contiguous()
+        out = torch.zeros_like(q)
+        cuda = q.is_cuda
+        if cuda:
+            main = torch.cuda.current_stream()
+            side = _side_stream(q.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.pair_forward(q, idx, d, None, mask, cfg.full_list, cfg.pair_pot, out=out)
+        else:
+            ops.pair_forward(q, idx, d, None, mask, cfg.full_list, cfg.pair_pot, out=out)
+        rho = ops.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, slab=(lay.x0, lay.nxl))
+        green = ops.make_green(scale=1.0, **cfg.green_args)
+        phi = cfg.filter.apply(rho, green)
+        if cuda:
+            main.wait_stream(side)
+        # out += 1/(2 Vol) * (partial gather); the self / background terms are added once, after
+        # the all-reduce
+        zero_dc = torch.zeros(q.shape[1], dtype=q.dtype, device=q.device)
+        epi = ops.make_epilogue(q, zero_dc, cfg.half_ivolume, 0.0, 0.0)
+        _, dvalues = ops.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=need_pos,
+                                values_out=out, epilogue=epi, slab=(lay.x0, lay.ns[0]))
+        if lay.world > 1:
+            dist.all_reduce(out, group=cfg.group)
+        out = out - q * cfg.self_half - cfg.background_ivolume * q.sum(dim=0)
+        ctx.cfg, ctx.pair_range, ctx.n_pairs = cfg, (lo, hi), n_pairs
+        ctx.save_for_backward(q, pos, d, idx, mask, dvalues)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        q, pos, d, idx, mask, dvalues = ctx.saved_tensors
+        cfg = ctx.cfg
+        ops, lay = cfg.ops, cfg.layout
+        need_q, need_pos, need_d = ctx.needs_input_grad[:3]
+        g = grad_out.contiguous()
+        n, c = q.shape
+        # one flat buffer so that a single all-reduce returns dL/dpositions and dL/dcharges
+        flat = torch.zeros(n * (3 + c), dtype=q.dtype, device=q.device)
+        g_pos = flat[: 3 * n].view(n, 3)
+        g_q = flat[3 * n:].view(n, c)
+        g_d = None
+        cuda = q.is_cuda
+        forked = False
+        if need_q or need_d:
+            lo, hi = ctx.pair_range
+            if need_d:
+                g_d = torch.zeros(ctx.n_pairs, dtype=q.dtype, device=q.device) if (hi - lo) != ctx.n_pairs \
+                    else torch.empty(ctx.n_pairs, dtype=q.dtype, device=q.device)
+            g_d_local = g_d[lo:hi] if need_d else None
+            if cuda:
+                main = torch.cuda.current_stream()
+                side = _side_stream(q.device)
+                side.wait_stream(main)
+                forked = True
+                with torch.cuda.stream(side):
+                    ops.pair_backward(q, idx, d, None, mask, g, cfg.full_list, cfg.pair_pot,
+                                      want_charges=need_q, want_pairs=need_d,
+                                      grad_charges_out=g_q if need_q else None, grad_pairs_out=g_d_local)
+            else:
+                ops.pair_backward(q, idx, d, None, mask, g, cfg.full_list, cfg.pair_pot,
+                                  want_charges=need_q, want_pairs=need_d,
+                                  grad_charges_out=g_q if need_q else None, grad_pairs_out=g_d_local)
+        if need_q or need_pos:
+            rho_g = ops.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, slab=(lay.x0, lay.nxl))
+            green = ops.make_green(scale=1.0, **cfg.green_args)
+            psi = cfg.filter.apply(rho_g, green)
+            if forked:
+                torch.cuda.current_stream().wait_stream(_side_stream(q.device))
+                forked = False
+            zero_dc = torch.zeros(c, dtype=q.dtype, device=q.device)
+            epi = ops.make_epilogue(g, zero_dc, cfg.half_ivolume, 0.0, 0.0,
+                                    coef2=g if need_pos else None, dvalues2=dvalues,
+                                    vjp_scale=cfg.half_ivolume)
+            slab = (lay.x0, lay.ns[0])
+            if need_pos:
+                ops.gather_vjp(psi, pos, q, cfg.r2u, cfg.nodes, cfg.method, grad_positions=g_pos,
+                               values_out=g_q if need_q else None, epilogue=epi, slab=slab)
+            else:
+                ops.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi, slab=slab)
+        if forked:
+            torch.cuda.current_stream().wait_stream(_side_stream(q.device))
+        if lay.world > 1:
+            dist.all_reduce(flat, group=cfg.group)
+        if need_q:
+            g_q = g_q - g * cfg.self_half - cfg.background_ivolume * g.sum(dim=0)
+        return (g_q if need_q else None), (g_pos if need_pos else None), g_d, None, None, None
+
+
+class _SlabMixin:
+    """
+    Adds ``process_group`` / ``transport`` / ``shard_pairs`` to a mesh calculator and routes
+    ``forward`` through the slab-decomposed pipeline.  Restrictions (checked): in-kernel
+    potentials (Coulomb, inverse power law), 3-D periodic, no cell / potential-parameter
+    gradients, power-of-two meshes whose x and y sizes are multiples of the world size.
+    """
+
+    def _init_slab(self, process_group, transport, shard_pairs, ops):
+        self.process_group = process_group
+        self.transport = transport
+        self.shard_pairs = shard_pairs
+        self._ops = ops or _native
+        self._slab_cfg = self._slab_key = None
+
+    def _world(self):
+        if not dist.is_available() or not dist.is_initialized():
+            raise RuntimeError("torch.distributed has to be initialised for the slab-decomposed calculators")
+        return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
+
+    def forward(self, charges, cell, positions, neighbor_indices, neighbor_distances,
+                periodic=None, node_mask=None, pair_mask=None, kvectors=None):
+        if node_mask is not None or kvectors is not None:
+            raise NotImplementedError("Batching not implemented for mesh-based calculators")
+        if periodic is not None:
+            raise NotImplementedError("the slab-decomposed calculators support 3-D periodic systems only")
+        validate_parameters(charges, cell, positions, neighbor_indices, neighbor_distances,
+                            periodic, pair_mask, node_mask, kvectors)
+        pot = self.potential
+        if pot._native_descriptor() is None:
+            raise NotImplementedError(
+                "the slab-decomposed calculators need an in-kernel potential "
+                "(CoulombPotential or InversePowerLawPotential)")
+        if cell.requires_grad or any(t.requires_grad for t in list(pot.parameters()) + list(pot.buffers())):
+            raise NotImplementedError(
+                "cell / potential-parameter gradients are not available in the slab-decomposed path")
+        world, rank = self._world()
+        if self._ops is _native and not positions.is_cuda:
+            raise _native.NativeLibraryError(
+                f"`positions` lives on {positions.device}; torchpme_b200 is a CUDA-only implementation "
+                "(no CPU fallback). Move the inputs to a CUDA device.")
+        geom = geometry_of(cell)
+        ns = geom.ns_mesh(self.mesh_spacing)
+        kind, exponent = pot._native_descriptor()
+        smearing, prefactor = pot._scalars()
+        n_channels = charges.shape[1]
+        key = (id(geom), ns, kind, exponent, smearing, prefactor, pot.exclusion_radius, pot.exclusion_degree,
+               self.full_neighbor_list, world, rank, n_channels, charges.dtype, charges.device)
+        cfg = self._slab_cfg if self._slab_key == key else None
+        if cfg is None:
+            ops = self._ops
+            cfg = _SlabStepConfig()
+            cfg.ops, cfg.group, cfg.shard_pairs = ops, self.process_group, self.shard_pairs
+            cfg.layout = SlabLayout(ns, world, rank)
+            cfg.r2u, cfg.ns = geom.r2u(ns), ns
+            cfg.nodes, cfg.method = self.interpolation_nodes, _native.METHOD_ID[self._method]
+            cfg.green_args = dict(kind=kind, exponent=exponent, smearing=smearing, prefactor=prefactor,
+                                  recip=geom.recip, spacing=geom.spacing(ns),
+                                  p3m_nodes=self.interpolation_nodes if self._method == "P3M" else 0)
+            cfg.pair_pot = ops.make_pair_potential(kind, smearing, prefactor, exponent,
+                                                   pot.exclusion_radius, pot.exclusion_degree)
+            cfg.full_list = self.full_neighbor_list
+            ivolume = 1.0 / geom.volume
+            cfg.half_ivolume = 0.5 * ivolume
+            cfg.self_half = 0.5 * float(pot.self_contribution())
+            cfg.background_ivolume = float(pot.background_correction()) * ivolume
+            cfg.filter = SlabFilter(cfg.layout, n_channels, charges.dtype, charges.device,
+                                    self.process_group, self.transport, ops)
+            self._slab_cfg, self._slab_key, self._slab_geom = cfg, key, geom
+        mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
+        return _SlabMeshPotential.apply(charges, positions, neighbor_distances, neighbor_indices,
+                                        mask_u8, cfg)
+
+
+class SlabPMECalculator(_SlabMixin, PMECalculator):
+    """:class:`PMECalculator` with the mesh slab-decomposed over the ranks of ``process_group``."""
+
+    def __init__(self, potential, mesh_spacing: float, interpolation_nodes: int = 4,
+                 full_neighbor_list: bool = False, process_group=None, transport: str = "nccl",
+                 shard_pairs: bool = True, _ops=None):
+        PMECalculator.__init__(self, potential, mesh_spacing, interpolation_nodes, full_neighbor_list)
+        self._init_slab(process_group, transport, shard_pairs, _ops)
+
+
+class SlabP3MCalculator(_SlabMixin, P3MCalculator):
+    """:class:`P3MCalculator` with the mesh slab-decomposed over the ranks of ``process_group``."""
+
+    def __init__(self, potential, mesh_spacing: float, interpolation_nodes: int = 4,
+                 full_neighbor_list: bool = False, process_group=None, transport: str = "nccl",
+                 shard_pairs: bool = True, _ops=None):
+        P3MCalculator.__init__(self, potential, mesh_spacing, interpolation_nodes, full_neighbor_list)
+        self._init_slab(process_group, transport, shard_pairs, _ops)
