@@ -280,6 +280,20 @@ def run_b200(args, wl):
             total_ms = float(t)
         return total_ms
 
+    if args.profile:
+        # kernel-level breakdown of a few eager steps (torch profiler / CUPTI), not a bench value
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                step()
+            torch.cuda.synchronize()
+        if rank == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(args.profile)), exist_ok=True)
+            with open(args.profile, "w") as f:
+                f.write(f"# torch.profiler, 5 eager steps, workload {args.workload}, {world} GPU(s), "
+                        f"decomposition {args.decomposition}, transport {args.transport}\n")
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -420,7 +434,11 @@ def run_b200(args, wl):
         }
         print(json.dumps(line), flush=True)
     if world > 1 or slab:
+        torch.cuda.synchronize()
+        if graphed is not None:
+            graphed.release()
         dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
@@ -435,6 +453,7 @@ def main():
     ap.add_argument("--decomposition", default="replica", choices=["replica", "slab"])
     ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
+    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 5 eager steps to this file")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

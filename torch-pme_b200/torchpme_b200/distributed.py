@@ -337,7 +337,8 @@ class _SlabMixin:
         self.transport = transport
         self.shard_pairs = shard_pairs
         self._ops = ops or _native
-        self._slab_cfg = self._slab_key = None
+        self._slab_cfg = None
+        self._slab_cfgs = {}
 
     def _world(self):
         if not dist.is_available() or not dist.is_initialized():
@@ -370,9 +371,12 @@ class _SlabMixin:
         kind, exponent = pot._native_descriptor()
         smearing, prefactor = pot._scalars()
         n_channels = charges.shape[1]
-        key = (id(geom), ns, kind, exponent, smearing, prefactor, pot.exclusion_radius, pot.exclusion_degree,
-               self.full_neighbor_list, world, rank, n_channels, charges.dtype, charges.device)
-        cfg = self._slab_cfg if self._slab_key == key else None
+        # keyed by the cell *values*: a clone of the same cell (e.g. the static buffer of a captured
+        # CUDA graph) must find the same exchange buffers again
+        key = (geom.cell.tobytes(), ns, kind, exponent, smearing, prefactor, pot.exclusion_radius,
+               pot.exclusion_degree, self.full_neighbor_list, world, rank, n_channels, charges.dtype,
+               charges.device)
+        cfg = self._slab_cfgs.get(key)
         if cfg is None:
             ops = self._ops
             cfg = _SlabStepConfig()
@@ -392,7 +396,10 @@ class _SlabMixin:
             cfg.background_ivolume = float(pot.background_correction()) * ivolume
             cfg.filter = SlabFilter(cfg.layout, n_channels, charges.dtype, charges.device,
                                     self.process_group, self.transport, ops)
-            self._slab_cfg, self._slab_key, self._slab_geom = cfg, key, geom
+            if len(self._slab_cfgs) >= 4:   # a captured graph keeps its own reference (GraphedStep)
+                self._slab_cfgs.pop(next(iter(self._slab_cfgs)))
+            self._slab_cfgs[key] = cfg
+        self._slab_cfg = cfg
         mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
         return _SlabMeshPotential.apply(charges, positions, neighbor_distances, neighbor_indices,
                                         mask_u8, cfg)

@@ -44,6 +44,13 @@ class GraphedStep:
                 self.energy, self.grad_positions, self.grad_distances = self._step()
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
+        # exchange buffers of a slab-decomposed calculator are baked into the graph: keep them alive
+        self._keepalive = getattr(calculator, "_slab_cfg", None)
+
+    def release(self) -> None:
+        """drop the captured graph (call before destroying a process group whose collectives it holds)"""
+        self.graph.reset()
+        self._keepalive = None
 
     def _step(self):
         V = self.calculator(self.charges, self.cell, self.positions, self.neighbor_indices,
