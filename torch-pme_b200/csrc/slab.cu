@@ -41,9 +41,14 @@ exchange_copy_kernel(const W* __restrict__ src, PeerPointers dst, int n_p, int n
   const int c = chunk / (n_a * n_p);
   const W* s = src + c * src_c + p * src_p + a * src_a;
   W* d = reinterpret_cast<W*>(dst.p[p]) + c * dst_c + a * dst_a;
-  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < run;
-       i += (int64_t)gridDim.y * blockDim.x)
-    d[i] = s[i];
+  // four independent 16-byte loads in flight per thread before the (possibly remote) stores
+  const int64_t stride = (int64_t)gridDim.y * blockDim.x;
+  int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < run; i += 4 * stride) {
+    const W v0 = s[i], v1 = s[i + stride], v2 = s[i + 2 * stride], v3 = s[i + 3 * stride];
+    d[i] = v0; d[i + stride] = v1; d[i + 2 * stride] = v2; d[i + 3 * stride] = v3;
+  }
+  for (; i < run; i += stride) d[i] = s[i];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -137,8 +142,8 @@ extern "C" int tpme_slab_exchange_copy(int elem_bytes, const void* src, void* co
   const int64_t words = (wide && elem_bytes == 8) ? run / 2 : run;
   const int div = (wide && elem_bytes == 8) ? 2 : 1;
   // enough CTAs to fill the machine (~8 per SM), at most one CTA per 256 words of a chunk
-  int64_t split = (8ll * num_sms() + chunks - 1) / chunks;
-  const int64_t max_split = (words + 255) / 256;
+  int64_t split = (4ll * num_sms() + chunks - 1) / chunks;
+  const int64_t max_split = (words + 1023) / 1024;
   if (split > max_split) split = max_split;
   if (split < 1) split = 1;
   if (split > 65535) split = 65535;
