@@ -451,7 +451,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decomposition", default="replica", choices=["replica", "slab"])
-    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p", "p2p-copy"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 5 eager steps to this file")
     args = ap.parse_args()

@@ -167,6 +167,26 @@ int tpme_slab_fft_x_green(int dtype, void* mesh_hat_t, int n_channels, int nx, i
 int tpme_slab_exchange_copy(int elem_bytes, const void* src, void* const* dst_host, int n_c, int n_p,
                             int n_a, int64_t run, int64_t src_c, int64_t src_p, int64_t src_a,
                             int64_t dst_c, int64_t dst_a, void* stream);
+/* Fused compute + exchange over peer memory.  `peers` lists, for every rank of the node, the
+ * x-slab array `hat[p]` (C, nx/W, ny, nz/2+1) and the y-slab array `hat_t[p]` (C, nx, ny/W, nz/2+1)
+ * as mapped into this process (tpme_peer_buffer_open).
+ *   tpme_slab_fft_yz_push       forward (y,z) passes of the local planes (scratch: hat[rank]); the
+ *                               y pass stores its results straight into hat_t of ALL ranks
+ *   tpme_slab_fft_x_green_push  x transform . G . inverse x transform of hat_t[rank]; the results
+ *                               are stored straight into hat of ALL ranks
+ * i.e. the all-to-all transposes travel as NVLink stores issued by the FFT kernels themselves
+ * while other thread blocks still compute; the caller separates the phases with
+ * tpme_peer_barrier. */
+typedef struct tpme_slab_peers {
+  int n_ranks, rank;
+  void* hat[TPME_MAX_RANKS];
+  void* hat_t[TPME_MAX_RANKS];
+} tpme_slab_peers;
+int tpme_slab_fft_yz_push(int dtype, void* real_mesh, int n_channels, int nx, int ny, int nz,
+                          const tpme_slab_peers* peers, void* stream);
+int tpme_slab_fft_x_green_push(int dtype, int n_channels, int nx, int ny, int nz,
+                               const tpme_green* green_host, const tpme_slab_peers* peers,
+                               void* stream);
 /* Peer-memory exchange buffers: cudaMalloc'ed, zero-filled, exported as a CUDA IPC handle that
  * the other ranks of the node open; and a device-side barrier over uint32 flags[n_ranks] that
  * live in such a buffer (`flags_host[p]` = rank p's flag array as mapped in this process,

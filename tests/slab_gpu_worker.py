@@ -40,7 +40,7 @@ def main():
         refs[method] = oracle.calculator_step(spec, q64.numpy(), cell64.numpy(), pos64.numpy(), idx_cpu.numpy(),
                                               d64.numpy(), mesh_spacing, 4, method, grad_out=gout64.numpy())
 
-    for transport in ("nccl", "p2p"):
+    for transport in ("nccl", "p2p", "p2p-copy"):
         for dtype in (torch.float64, torch.float32):
             for method in ("P3M", "Lagrange"):
                 if method == "P3M":
@@ -59,7 +59,7 @@ def main():
                 dd = d.grad.clone()
                 dist.all_reduce(dd)
                 ref = refs[method]
-                if transport == "p2p":
+                if transport.startswith("p2p"):
                     calc._slab_cfg.filter.exchange.check()
 
                 def err(a, b):

@@ -88,6 +88,22 @@ def test_virtual_ranks_reproduce_single_gpu(method, nodes, channels, ns, world, 
         phi.append(out)
     assert rel_err(torch.cat(phi, dim=1), phi_full) < tol
 
+    # ---- the same through the fused compute + exchange kernels (y pass / x pass push to the "peers")
+    for t in X + T:
+        t.fill_(float("nan"))
+    for r in range(world):
+        peers = _native.make_slab_peers(r, [t.data_ptr() for t in X], [t.data_ptr() for t in T])
+        _native.slab_fft_yz_push(rho[r], ns, peers)
+    for r in range(world):
+        peers = _native.make_slab_peers(r, [t.data_ptr() for t in X], [t.data_ptr() for t in T])
+        _native.slab_fft_x_green_push(dtype, torch.device(dev), channels, ns, green, peers)
+    phi2 = []
+    for r in range(world):
+        out = torch.empty_like(rho[r])
+        _native.slab_fft_yz(False, out, X[r])
+        phi2.append(out)
+    assert rel_err(torch.cat(phi2, dim=1), phi_full) < tol
+
     # ---- gather: partial sums over the slabs == full gather (values, dV/dr, vjp)
     v_full, dv_full = _native.gather(phi_full, pos, r2u, nodes, mid, want_grad=True)
     gp_full, _, _ = _native.gather_vjp(phi_full, pos, w, r2u, nodes, mid)
@@ -113,7 +129,7 @@ def world1_group():
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+@pytest.mark.parametrize("transport", ["nccl", "p2p", "p2p-copy"])
 @pytest.mark.parametrize("method, dtype", [("P3M", torch.float32), ("Lagrange", torch.float64)])
 def test_world_size_one_matches_plain_calculator(world1_group, method, dtype, transport):
     import torchpme_b200 as tp

@@ -58,6 +58,17 @@ __device__ __forceinline__ double rint_t(double x) { return rint(x); }
 __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
 __device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }
 
+// Optional redirection of the final stores of a strided FFT pass into the buffers of other GPUs
+// (slab decomposition: the transposing all-to-all is fused into the FFT pass, the results travel
+// as NVLink peer stores while other CTAs still compute).  Line `l` of work item `o` goes to
+//   p[l >> shift] + (o / dA) * sA + (o % dA) * sB + (l & ((1 << shift) - 1)) * sL + off + z
+constexpr int kMaxRanks = 16;
+struct RemoteStore {
+  void* p[kMaxRanks];
+  int enabled, shift, dA;
+  int64_t sA, sB, sL, off;
+};
+
 inline int num_sms() {
   static int cached = 0;
   if (!cached) {

@@ -21,6 +21,7 @@
 //   * G(k) is evaluated from per-CTA axis tables (k = a[ix] + b[iy,iz], sines by angle addition),
 //     one exp and one division per k-point.
 #pragma once
+#include <cstring>
 #include "common.cuh"
 #include "green.cuh"
 
@@ -239,7 +240,7 @@ template <typename T, typename GT, int N, int MODE, int GV>
 __global__ void __launch_bounds__(MaxThreads<T>::value)
 lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, int64_t ls, int d1,
                  int64_t s1, int64_t s0, GreenDev<GT> green, int nx, int ny, int nz, T* __restrict__ dc_out,
-                 int y_off) {
+                 int y_off, RemoteStore rs) {
   using CH = Chain<N>;
   constexpr int NG = CH::NG, RA = CH::RA, RB = CH::RB, RL = CH::RL;
   constexpr int QA = N / RA;                 // element spacing inside the first DIF group
@@ -254,6 +255,15 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
   const int cols = min(zc, n_inner - z0);
   const int o_hi = o / d1, o_lo = o - o_hi * d1;
   C2<T>* base = data + o_hi * s1 + o_lo * s0 + z0;
+  // final stores: in place, or into the peers' buffers
+  const int64_t r_base = rs.enabled ? (int64_t)(o / rs.dA) * rs.sA + (int64_t)(o % rs.dA) * rs.sB + rs.off + z0 : 0;
+  const int r_mask = (1 << rs.shift) - 1;
+  auto store_line = [&](int line, int c, C2<T> v) {
+    if (rs.enabled)
+      (reinterpret_cast<C2<T>*>(rs.p[line >> rs.shift]) + r_base)[(int64_t)(line & r_mask) * rs.sL + c] = v;
+    else
+      base[(int64_t)line * ls + c] = v;
+  };
 
   if (NG > 1) fill_twiddles<T, N>(tw, tid, nt);
   if (MODE == 2 && GV != GV_GENERIC) {
@@ -293,10 +303,10 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
           }
           dit_regs<T, N, 1, RA, +1, 1>(v, 0, tw);
 #pragma unroll
-          for (int i = 0; i < RA; ++i) base[(int64_t)i * ls + c] = v[i];
+          for (int i = 0; i < RA; ++i) store_line(i, c, v[i]);
         } else {
 #pragma unroll
-          for (int i = 0; i < RA; ++i) base[(int64_t)bitrev<N>(i) * ls + c] = v[i];
+          for (int i = 0; i < RA; ++i) store_line(bitrev<N>(i), c, v[i]);
         }
       } else {
 #pragma unroll
@@ -350,7 +360,7 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
       dif_regs<T, N, RL, RL, -1, 1>(v, 0, tw);
       if (MODE == 0) {
 #pragma unroll
-        for (int i = 0; i < RL; ++i) base[(int64_t)bitrev<N>(blk * RL + i) * ls + c] = v[i];
+        for (int i = 0; i < RL; ++i) store_line(bitrev<N>(blk * RL + i), c, v[i]);
       } else {
         AxisEntry<GT> eb;
         if (GV != GV_GENERIC) eb = ax_b[c];
@@ -401,7 +411,7 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
     for (int i = 0; i < RA; ++i) v[i] = tile[(j0 + i * QA) * zc + c];
     dit_regs<T, N, QA, RA, +1, 1>(v, j0, tw);
 #pragma unroll
-    for (int i = 0; i < RA; ++i) base[(int64_t)(j0 + i * QA) * ls + c] = v[i];
+    for (int i = 0; i < RA; ++i) store_line(j0 + i * QA, c, v[i]);
   }
 }
 
@@ -839,7 +849,8 @@ int dispatch_rows(int nz, bool forward, const void* in, void* out, int64_t n_row
 
 template <typename T, typename GT, int N, int MODE, int GV>
 int launch_lines(void* data, int n_outer, int n_inner, int64_t ls, int d1, int64_t s1, int64_t s0,
-                 const GreenDev<GT>& green, int nx, int ny, int nz, void* dc_out, cudaStream_t s, int y_off = 0) {
+                 const GreenDev<GT>& green, int nx, int ny, int nz, void* dc_out, cudaStream_t s, int y_off = 0,
+                 const RemoteStore* rs = nullptr) {
   // columns per CTA: one first-group radix item per thread, at least ~2 CTAs per SM when the
   // mesh is small, never narrower than 8 columns (64-byte runs)
   constexpr int items_per_col = N / Chain<N>::RA > 0 ? N / Chain<N>::RA : 1;
@@ -858,17 +869,21 @@ int launch_lines(void* data, int n_outer, int n_inner, int64_t ls, int d1, int64
   if (MODE == 2) smem += ((size_t)N + zc) * sizeof(AxisEntry<GT>);
   auto kernel = lines_fft_kernel<T, GT, N, MODE, GV>;
   if (int rc = allow_smem(kernel, smem)) return rc;
+  RemoteStore remote;
+  if (rs != nullptr) remote = *rs;
+  else memset(&remote, 0, sizeof(remote));
   kernel<<<(unsigned)(n_outer * n_chunks), threads, smem, s>>>(
-      (C2<T>*)data, n_inner, zc, n_chunks, ls, d1, s1, s0, green, nx, ny, nz, (T*)dc_out, y_off);
+      (C2<T>*)data, n_inner, zc, n_chunks, ls, d1, s1, s0, green, nx, ny, nz, (T*)dc_out, y_off, remote);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <typename T, typename GT, int MODE, int GV>
 int dispatch_lines(int n, void* data, int n_outer, int n_inner, int64_t ls, int d1, int64_t s1, int64_t s0,
-                   const GreenDev<GT>& green, int nx, int ny, int nz, void* dc_out, cudaStream_t s, int y_off = 0) {
+                   const GreenDev<GT>& green, int nx, int ny, int nz, void* dc_out, cudaStream_t s, int y_off = 0,
+                   const RemoteStore* rs = nullptr) {
 #define TPME_LINES(NN) \
-  case NN: return launch_lines<T, GT, NN, MODE, GV>(data, n_outer, n_inner, ls, d1, s1, s0, green, nx, ny, nz, dc_out, s, y_off);
+  case NN: return launch_lines<T, GT, NN, MODE, GV>(data, n_outer, n_inner, ls, d1, s1, s0, green, nx, ny, nz, dc_out, s, y_off, rs);
   switch (n) {
     TPME_LINES(8) TPME_LINES(16) TPME_LINES(32) TPME_LINES(64) TPME_LINES(128) TPME_LINES(256) TPME_LINES(512)
   }
@@ -923,7 +938,7 @@ int green_variant(const GreenDev<GT>& g) {
 // y0 .. y0 + ny_local - 1 of the global mesh (ny_local == ny, y0 == 0: the whole mesh)
 template <typename T, typename GT, bool FAST>
 int x_pass_green(void* hat, int channels, int nx, int ny, int nz, int y0, int ny_local,
-                 const GreenDev<GT>& green_in, void* dc_out, cudaStream_t s) {
+                 const GreenDev<GT>& green_in, void* dc_out, cudaStream_t s, const RemoteStore* rs = nullptr) {
   const int nzh = nz / 2 + 1;
   GreenDev<GT> green = green_in;
   const int gv = FAST ? green_variant(green) : (int)GV_GENERIC;
@@ -933,7 +948,7 @@ int x_pass_green(void* hat, int channels, int nx, int ny, int nz, int y0, int ny
   int rc = 0;
 #define TPME_XPASS(GV)                                                                                   \
   rc = dispatch_lines<T, GT, 2, GV>(nx, hat, channels * ny_local, nzh, (int64_t)ny_local * nzh, ny_local, \
-                                    (int64_t)nx * ny_local * nzh, nzh, green, nx, ny, nz, dc_out, s, y0)
+                                    (int64_t)nx * ny_local * nzh, nzh, green, nx, ny, nz, dc_out, s, y0, rs)
   if (FAST && gv == GV_ORTHO) TPME_XPASS(GV_ORTHO);
   else if (FAST && gv == GV_TRI) TPME_XPASS(GV_TRI);
   else if (FAST && gv == GV_TRI_P3M) TPME_XPASS(GV_TRI_P3M);
@@ -946,17 +961,19 @@ int x_pass_green(void* hat, int channels, int nx, int ny, int nz, int y0, int ny
 // (planes, ny, nz/2+1) when `forward`, the reverse otherwise (the half-complex input is destroyed).
 // Fused per-plane kernel when the plane fits in shared memory, separate z / y passes otherwise.
 template <typename T, typename GT>
-int yz_passes(bool forward, void* real, void* hat, int planes, int ny, int nz, cudaStream_t s) {
+int yz_passes(bool forward, void* real, void* hat, int planes, int ny, int nz, cudaStream_t s,
+              const RemoteStore* rs = nullptr) {
   const int nzh = nz / 2 + 1;
   const int64_t rows = (int64_t)planes * ny;
   GreenDev<GT> unused{};
   if (forward) {
-    const int prc = dispatch_plane<T>(ny, nz, true, real, hat, planes, s);
+    // with a remote destination the separate z / y passes are used: only their y pass can push
+    const int prc = rs != nullptr ? -1 : dispatch_plane<T>(ny, nz, true, real, hat, planes, s);
     if (prc >= 0) return prc;
     if (int rc = dispatch_rows<T>(nz, true, real, hat, rows, s)) return rc;
     // y pass: outer = (c, x), line stride nzh
     return dispatch_lines<T, GT, 0, GV_GENERIC>(ny, hat, planes, nzh, nzh, 1 << 30, 0, (int64_t)ny * nzh,
-                                                unused, 0, ny, nz, nullptr, s);
+                                                unused, 0, ny, nz, nullptr, s, 0, rs);
   }
   const int prc = dispatch_plane<T>(ny, nz, false, hat, real, planes, s);
   if (prc >= 0) return prc;

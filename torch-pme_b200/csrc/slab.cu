@@ -16,11 +16,18 @@
 
 namespace tpme {
 
-int slab_yz_f32(bool, void*, void*, int, int, int, cudaStream_t);
-int slab_yz_f64(bool, void*, void*, int, int, int, cudaStream_t);
-int slab_x_f32(void*, int, int, int, int, int, int, const GreenDev<float>&, void*, cudaStream_t);
-int slab_x_f64(void*, int, int, int, int, int, int, const GreenDev<double>&, void*, cudaStream_t);
-int slab_x_f32d(void*, int, int, int, int, int, int, const GreenDev<double>&, void*, cudaStream_t);
+int slab_yz_f32(bool, void*, void*, int, int, int, cudaStream_t, const RemoteStore*);
+int slab_yz_f64(bool, void*, void*, int, int, int, cudaStream_t, const RemoteStore*);
+int slab_x_f32(void*, int, int, int, int, int, int, const GreenDev<float>&, void*, cudaStream_t, const RemoteStore*);
+int slab_x_f64(void*, int, int, int, int, int, int, const GreenDev<double>&, void*, cudaStream_t, const RemoteStore*);
+int slab_x_f32d(void*, int, int, int, int, int, int, const GreenDev<double>&, void*, cudaStream_t, const RemoteStore*);
+static_assert(kMaxRanks == TPME_MAX_RANKS, "rank limit of the kernels and of the ABI differ");
+
+static int ilog2_exact(int n) {
+  int s = 0;
+  while ((1 << s) < n) ++s;
+  return (1 << s) == n ? s : -1;
+}
 
 static bool pow2_dim(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
 
@@ -98,8 +105,81 @@ extern "C" int tpme_slab_fft_yz(int dtype, int forward, void* real_mesh, void* m
                "the slab-decomposed FFT needs power-of-two mesh dimensions in 8..512");
   if (n_planes <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  return dtype == 0 ? slab_yz_f32(forward != 0, real_mesh, mesh_hat, n_planes, ny, nz, s)
-                    : slab_yz_f64(forward != 0, real_mesh, mesh_hat, n_planes, ny, nz, s);
+  return dtype == 0 ? slab_yz_f32(forward != 0, real_mesh, mesh_hat, n_planes, ny, nz, s, nullptr)
+                    : slab_yz_f64(forward != 0, real_mesh, mesh_hat, n_planes, ny, nz, s, nullptr);
+}
+
+static int check_peers(const tpme_slab_peers* peers, int nx, int ny) {
+  TPME_REQUIRE(peers != nullptr, "peer table missing");
+  TPME_REQUIRE(peers->n_ranks > 0 && peers->n_ranks <= TPME_MAX_RANKS && peers->rank >= 0 &&
+               peers->rank < peers->n_ranks, "bad rank layout");
+  TPME_REQUIRE(nx % peers->n_ranks == 0 && ny % peers->n_ranks == 0, "the world size has to divide nx and ny");
+  for (int p = 0; p < peers->n_ranks; ++p)
+    TPME_REQUIRE(peers->hat[p] != nullptr && peers->hat_t[p] != nullptr, "null peer buffer");
+  return 0;
+}
+
+// forward (y,z) passes of the local x planes; the y pass stores its output straight into the
+// y-slab arrays of all ranks (rank p receives the rows [p ny/W, (p+1) ny/W))
+extern "C" int tpme_slab_fft_yz_push(int dtype, void* real_mesh, int n_channels, int nx, int ny,
+                                     int nz, const tpme_slab_peers* peers, void* stream) {
+  TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 or 1");
+  TPME_REQUIRE(pow2_dim(nx) && pow2_dim(ny) && pow2_dim(nz),
+               "the slab-decomposed FFT needs power-of-two mesh dimensions in 8..512");
+  if (int rc = check_peers(peers, nx, ny)) return rc;
+  if (n_channels <= 0) return 0;
+  const int w = peers->n_ranks, rank = peers->rank;
+  const int nxl = nx / w, nyl = ny / w, nzh = nz / 2 + 1;
+  RemoteStore rs;
+  memset(&rs, 0, sizeof(rs));
+  for (int p = 0; p < w; ++p) rs.p[p] = peers->hat_t[p];
+  rs.enabled = 1;
+  rs.shift = ilog2_exact(nyl);
+  TPME_REQUIRE(rs.shift >= 0, "rows per rank must be a power of two");
+  // work item o = c * nxl + xl  ->  (c * nx + rank * nxl + xl) * nyl * nzh + yl * nzh + z
+  rs.dA = nxl;
+  rs.sA = (int64_t)nx * nyl * nzh;
+  rs.sB = (int64_t)nyl * nzh;
+  rs.sL = nzh;
+  rs.off = (int64_t)rank * nxl * nyl * nzh;
+  cudaStream_t s = (cudaStream_t)stream;
+  void* scratch = peers->hat[rank];
+  return dtype == 0 ? slab_yz_f32(true, real_mesh, scratch, n_channels * nxl, ny, nz, s, &rs)
+                    : slab_yz_f64(true, real_mesh, scratch, n_channels * nxl, ny, nz, s, &rs);
+}
+
+// x pass . G . inverse x pass on the local y rows; the results are stored straight into the
+// x-slab arrays of all ranks (rank p receives the planes [p nx/W, (p+1) nx/W))
+extern "C" int tpme_slab_fft_x_green_push(int dtype, int n_channels, int nx, int ny, int nz,
+                                          const tpme_green* green, const tpme_slab_peers* peers,
+                                          void* stream) {
+  TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 or 1");
+  TPME_REQUIRE(pow2_dim(nx), "the slab-decomposed FFT needs power-of-two mesh dimensions in 8..512");
+  if (int rc = check_peers(peers, nx, ny)) return rc;
+  if (int rc = check_green(green)) return rc;
+  if (n_channels <= 0) return 0;
+  const int w = peers->n_ranks, rank = peers->rank;
+  const int nxl = nx / w, nyl = ny / w, nzh = nz / 2 + 1;
+  RemoteStore rs;
+  memset(&rs, 0, sizeof(rs));
+  for (int p = 0; p < w; ++p) rs.p[p] = peers->hat[p];
+  rs.enabled = 1;
+  rs.shift = ilog2_exact(nxl);
+  TPME_REQUIRE(rs.shift >= 0, "planes per rank must be a power of two");
+  // work item o = c * nyl + yl  ->  (c * nxl + xl) * ny * nzh + (rank * nyl + yl) * nzh + z
+  rs.dA = nyl;
+  rs.sA = (int64_t)nxl * ny * nzh;
+  rs.sB = nzh;
+  rs.sL = (int64_t)ny * nzh;
+  rs.off = (int64_t)rank * nyl * nzh;
+  cudaStream_t s = (cudaStream_t)stream;
+  void* hat_t = peers->hat_t[rank];
+  const int y0 = rank * nyl;
+  if (dtype == 1)
+    return slab_x_f64(hat_t, n_channels, nx, ny, nz, y0, nyl, make_green<double>(green), nullptr, s, &rs);
+  if (needs_double_math(green))
+    return slab_x_f32d(hat_t, n_channels, nx, ny, nz, y0, nyl, make_green<double>(green), nullptr, s, &rs);
+  return slab_x_f32(hat_t, n_channels, nx, ny, nz, y0, nyl, make_green<float>(green), nullptr, s, &rs);
 }
 
 extern "C" int tpme_slab_fft_x_green(int dtype, void* mesh_hat_t, int n_channels, int nx, int ny,
@@ -112,10 +192,10 @@ extern "C" int tpme_slab_fft_x_green(int dtype, void* mesh_hat_t, int n_channels
   if (n_channels <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == 1)
-    return slab_x_f64(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<double>(green), nullptr, s);
+    return slab_x_f64(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<double>(green), nullptr, s, nullptr);
   if (needs_double_math(green))
-    return slab_x_f32d(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<double>(green), nullptr, s);
-  return slab_x_f32(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<float>(green), nullptr, s);
+    return slab_x_f32d(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<double>(green), nullptr, s, nullptr);
+  return slab_x_f32(mesh_hat_t, n_channels, nx, ny, nz, y0, ny_local, make_green<float>(green), nullptr, s, nullptr);
 }
 
 extern "C" int tpme_slab_exchange_copy(int elem_bytes, const void* src, void* const* dst_host,

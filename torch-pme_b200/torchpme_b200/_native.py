@@ -70,6 +70,15 @@ class _PointEpilogue(ctypes.Structure):
     ]
 
 
+class _SlabPeers(ctypes.Structure):
+    _fields_ = [
+        ("n_ranks", ctypes.c_int),
+        ("rank", ctypes.c_int),
+        ("hat", ctypes.c_void_p * 16),
+        ("hat_t", ctypes.c_void_p * 16),
+    ]
+
+
 _vp, _i, _i64, _dp = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)
 
 #: every symbol the header declares, with its argument types (used by the loader and by
@@ -91,6 +100,8 @@ SIGNATURES = {
     "tpme_slab_fft_x_green": ([_i, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
     "tpme_slab_exchange_copy": ([_i, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
                                  _i64, _vp], _i),
+    "tpme_slab_fft_yz_push": ([_i, _vp, _i, _i, _i, _i, ctypes.POINTER(_SlabPeers), _vp], _i),
+    "tpme_slab_fft_x_green_push": ([_i, _i, _i, _i, _i, ctypes.POINTER(_Green), ctypes.POINTER(_SlabPeers), _vp], _i),
     "tpme_peer_buffer_create": ([_i64, ctypes.POINTER(_vp), ctypes.c_char_p], _i),
     "tpme_peer_buffer_open": ([ctypes.c_char_p, ctypes.POINTER(_vp)], _i),
     "tpme_peer_buffer_close": ([_vp], _i),
@@ -441,6 +452,36 @@ def slab_exchange_copy(src, dst_ptrs, n_c, n_p, n_a, run, src_strides, dst_strid
                                            src_strides[0], src_strides[1], src_strides[2],
                                            dst_strides[0], dst_strides[1], _stream()),
                "tpme_slab_exchange_copy")
+    _count()
+
+
+def make_slab_peers(rank: int, hat_ptrs, hat_t_ptrs) -> _SlabPeers:
+    peers = _SlabPeers()
+    peers.n_ranks, peers.rank = len(hat_ptrs), int(rank)
+    for p, (a, b) in enumerate(zip(hat_ptrs, hat_t_ptrs)):
+        peers.hat[p], peers.hat_t[p] = int(a), int(b)
+    return peers
+
+
+def slab_fft_yz_push(real_mesh, ns, peers: _SlabPeers):
+    """forward (y,z) passes of the local planes, results stored into the y-slab arrays of all ranks"""
+    lib = load()
+    nx, ny, nz = ns
+    c = real_mesh.shape[0]
+    with _on(real_mesh, "mesh"):
+        _check(lib.tpme_slab_fft_yz_push(_dtype_id(real_mesh), _dev(real_mesh, "mesh"), c, nx, ny, nz,
+                                         ctypes.byref(peers), _stream()), "tpme_slab_fft_yz_push")
+    _count(2)
+
+
+def slab_fft_x_green_push(dtype, device, n_channels: int, ns, green: _Green, peers: _SlabPeers):
+    """x pass . G . inverse x pass of the local y rows, results stored into the x-slab arrays of all ranks"""
+    lib = load()
+    nx, ny, nz = ns
+    with torch.cuda.device(device):
+        _check(lib.tpme_slab_fft_x_green_push(0 if dtype == torch.float32 else 1, n_channels, nx, ny, nz,
+                                              ctypes.byref(green), ctypes.byref(peers), _stream()),
+               "tpme_slab_fft_x_green_push")
     _count()
 
 

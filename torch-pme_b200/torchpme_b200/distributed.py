@@ -11,10 +11,11 @@ potentials back.  Inside:
   slab (``tpme_spread_slab``) -- no halo, no reduction;
 * **FFT . G . iFFT**: local (y,z) passes, exchange x slabs -> y slabs, x pass fused with the
   Green's function on the local y rows, exchange back, inverse (y,z) passes.  The exchange is
-  either NCCL ``all_to_all_single`` around a packing copy kernel (``transport="nccl"``) or a
-  single copy kernel that stores straight into the peers' receive buffers over NVLink
-  followed by a device-side flag barrier (``transport="p2p"``: pack + transfer + unpack in one
-  kernel, no library call);
+  * ``transport="p2p"``: fused into the FFT kernels -- the y pass and the x pass store their
+    results straight into the peers' arrays over NVLink (CUDA IPC mappings) while other thread
+    blocks still compute, followed by a device-side flag barrier; no copy kernel, no library call;
+  * ``transport="p2p-copy"``: one copy kernel that packs, transfers (peer stores) and unpacks;
+  * ``transport="nccl"``: ``all_to_all_single`` between a packing and an unpacking copy kernel;
 * **gather**: partial sums over the local planes (``tpme_gather_slab``); they are summed over
   the ranks by the same all-reduce that combines the real-space pair sum, whose pair list is
   cut into ``W`` contiguous chunks;
@@ -154,7 +155,21 @@ class PeerExchange:
         self.hat_t = self.buffer.as_tensor(self._off_t, (channels, nx, layout.nyl, layout.nzh, 2), dtype)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        self.dtype, self.device = dtype, device
+        self.peers = _native.make_slab_peers(layout.rank, [b + self._off_x for b in self.peer_base],
+                                             [b + self._off_t for b in self.peer_base])
         dist.barrier(group=group)   # every rank has mapped every buffer before the first store
+
+    # fused compute + exchange: the FFT passes store their results into the peers' arrays
+    def push_yz(self, rho_local):
+        _native.slab_fft_yz_push(rho_local, self.layout.ns, self.peers)
+        self._barrier()
+        return self.hat_t
+
+    def push_x_green(self, green):
+        _native.slab_fft_x_green_push(self.dtype, self.device, self.c, self.layout.ns, green, self.peers)
+        self._barrier()
+        return self.hat
 
     def _barrier(self):
         _native.peer_barrier(self.peer_base, self.layout.rank, self.epoch, self.error)
@@ -194,20 +209,27 @@ class SlabFilter:
     def __init__(self, layout: SlabLayout, channels: int, dtype, device, group, transport="nccl",
                  ops=None):
         self.layout, self.ops = layout, ops or _native
-        if transport == "p2p":
+        self.fused = False
+        if transport in ("p2p", "p2p-copy"):
             self.exchange = PeerExchange(layout, channels, dtype, device, group, self.ops)
+            self.fused = transport == "p2p"
         elif transport == "nccl":
             self.exchange = NcclExchange(layout, channels, dtype, device, group, self.ops)
         else:
-            raise ValueError(f"unknown transport '{transport}' (choose 'nccl' or 'p2p')")
+            raise ValueError(f"unknown transport '{transport}' (choose 'nccl', 'p2p' or 'p2p-copy')")
 
     def apply(self, rho_local: torch.Tensor, green) -> torch.Tensor:
         """``rho_local`` (C, nxl, ny, nz) -> filtered slab of the same shape"""
         ex, lay, ops = self.exchange, self.layout, self.ops
-        ops.slab_fft_yz(True, rho_local, ex.hat)
-        hat_t = ex.x_to_y()
-        ops.slab_fft_x_green(hat_t, lay.ns, lay.y0, green)
-        hat = ex.y_to_x()
+        if self.fused:
+            # transport "p2p": the y pass and the x pass push their results to the peers themselves
+            ex.push_yz(rho_local)
+            hat = ex.push_x_green(green)
+        else:
+            ops.slab_fft_yz(True, rho_local, ex.hat)
+            hat_t = ex.x_to_y()
+            ops.slab_fft_x_green(hat_t, lay.ns, lay.y0, green)
+            hat = ex.y_to_x()
         out = torch.empty_like(rho_local)
         ops.slab_fft_yz(False, out, hat)
         return out
