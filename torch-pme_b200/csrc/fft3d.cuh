@@ -237,7 +237,7 @@ __device__ __forceinline__ int skew(int p) { return p + (p >> 4); }
 template <typename T> struct MaxThreads { static constexpr int value = sizeof(T) == 8 ? 128 : 256; };
 
 template <typename T, typename GT, int N, int MODE, int GV>
-__global__ void __launch_bounds__(MaxThreads<T>::value)
+__global__ void __launch_bounds__(MaxThreads<T>::value, (sizeof(T) == 4 && MODE == 2 && GV == GV_ORTHO) ? 3 : 1)
 lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, int64_t ls, int d1,
                  int64_t s1, int64_t s0, GreenDev<GT> green, int nx, int ny, int nz, T* __restrict__ dc_out,
                  int y_off, RemoteStore rs) {
