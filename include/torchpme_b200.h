@@ -198,6 +198,13 @@ int tpme_peer_buffer_close(void* dev_ptr);
 int tpme_peer_buffer_destroy(void* dev_ptr);
 int tpme_peer_barrier(void* const* flags_host, int n_ranks, int rank, void* epoch,
                       double timeout_seconds, void* error_flag, void* stream);
+/* Sum all-reduce of `n` reals over peer memory (combines the partial potentials / gradients of
+ * the slabs and pair-list chunks): rank r pulls slice r of every rank's input region, sums in
+ * rank order and stores the result into slice r of every rank's output region, so all ranks
+ * hold bitwise identical sums.  `in_host[p]` / `out_host[p]`: rank p's regions as mapped in this
+ * process, 16-byte aligned and padded to a multiple of 16 bytes.  Bracket with tpme_peer_barrier. */
+int tpme_peer_allreduce(int dtype, void* const* in_host, void* const* out_host, int n_ranks, int rank,
+                        int64_t n, void* stream);
 
 /* ---- real space -----------------------------------------------------------------------
  * replaces Calculator._compute_rspace (src/torchpme/calculators/calculator.py:43-87) and

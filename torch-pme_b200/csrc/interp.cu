@@ -58,6 +58,25 @@ __device__ __forceinline__ void point_stencil(const T* __restrict__ pos, const M
   }
 }
 
+// first stencil node of one axis only, and whether the N planes starting there reach into the
+// local x slab [x0, x0 + nxl): lets slab-decomposed kernels drop foreign points before any
+// weight is evaluated
+template <typename T, int N>
+__device__ __forceinline__ int axis_first(const T* __restrict__ pos, const Mat3<T>& r2u,
+                                          const MeshDims<T>& dims, int a) {
+  const T u = pos[0] * r2u.m[a] + pos[1] * r2u.m[3 + a] + pos[2] * r2u.m[6 + a];
+  const T base = (N % 2 == 0) ? floor_t(u) : rint_t(u);
+  return wrap_base<T>(base + T(1 - (N + 1) / 2), dims.n[a], dims.inv_n[a]);
+}
+
+__device__ __forceinline__ bool touches_slab(int first, int nodes, int nx, int x0, int nxl) {
+  int ahead = first - x0;      // (first - x0) mod nx < nxl: the first plane lies inside
+  if (ahead < 0) ahead += nx;
+  int behind = x0 - first;     // (x0 - first) mod nx < nodes: the slab starts inside the stencil
+  if (behind < 0) behind += nx;
+  return ahead < nxl || behind < nodes;
+}
+
 template <typename T, int N>
 __device__ __forceinline__ T pick(const T (&arr)[N], int k) {
   T out = arr[0];
@@ -90,11 +109,12 @@ spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, in
   if (point >= n_points) return;
   const int c = (int)(tid - point * G);
   if (c >= N) return;
+  const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
+  if (nxl < nx && !touches_slab(axis_first<T, N>(positions + 3 * point, r2u, dims, 0), N, nx, x0, nxl)) return;
 
   int first[3];
   T w[3][N], dw[3][N];
   point_stencil<T, METHOD, N, false>(positions + 3 * point, r2u, dims, first, w, dw);
-  const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
   const unsigned plane = (unsigned)ny * nz;
   const int64_t mesh_size = (int64_t)plane * nxl;   // the local slab holds x planes x0 .. x0 + nxl - 1
   unsigned xoff[N], yoff[N];
@@ -339,34 +359,32 @@ gather_point_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
   if (!valid && !((MODE & 4) && grad_r2u != nullptr)) return;
   const int64_t point = valid ? point_raw : n_points - 1;
 
-  int first[3];
-  T w[3][N], dw[3][N];
-  point_stencil<T, METHOD, N, DERIV>(positions + 3 * point, r2u, dims, first, w, dw);
   const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
   const unsigned plane = (unsigned)ny * nz;
   const int64_t mesh_size = (int64_t)plane * nxl;
+  int first[3];
+  T w[3][N], dw[3][N];
   unsigned xoff[N], yoff[N];
-  bool any_inside = false;
-  {
+  unsigned zoff[NV];
+  T wz[W], dwz[W];
+  bool any_inside = nxl >= nx ||
+                    touches_slab(axis_first<T, N>(positions + 3 * point, r2u, dims, 0), N, nx, x0, nxl);
+  if (any_inside) {
+    point_stencil<T, METHOD, N, DERIV>(positions + 3 * point, r2u, dims, first, w, dw);
     int ix = first[0], iy = first[1];
 #pragma unroll
     for (int a = 0; a < N; ++a) {
       const unsigned lx = (unsigned)(ix - x0);
       const bool inside = lx < (unsigned)nxl;
-      any_inside |= inside;
       xoff[a] = inside ? lx * plane : 0u;
       if (!inside) { w[0][a] = T(0); if (DERIV) dw[0][a] = T(0); }
       yoff[a] = (unsigned)iy * nz;
       ix = (ix + 1 >= nx) ? wrap_add(ix + 1, nx) : ix + 1;
       iy = (iy + 1 >= ny) ? wrap_add(iy + 1, ny) : iy + 1;
     }
-  }
-  // z window: aligned vectors, weights shifted by o = first[2] mod VEC
-  const int zb = first[2] & ~(VEC - 1);
-  const int o = first[2] - zb;
-  unsigned zoff[NV];
-  T wz[W], dwz[W];
-  {
+    // z window: aligned vectors, weights shifted by o = first[2] mod VEC
+    const int zb = first[2] & ~(VEC - 1);
+    const int o = first[2] - zb;
     int z = zb;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {

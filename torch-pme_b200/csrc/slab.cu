@@ -94,6 +94,31 @@ __global__ void peer_barrier_kernel(PeerPointers flags, int n_ranks, int rank, u
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// all-reduce (sum) over peer memory in one kernel: rank r pulls slice r of every rank's input
+// region (W loads in flight per thread), sums them in rank order and pushes the result into slice
+// r of every rank's output region.  Every element is reduced by exactly one rank, so all ranks
+// end up with bitwise identical sums.  The caller brackets the kernel with peer barriers.
+// ---------------------------------------------------------------------------------------
+template <typename V, typename T, int VEC>
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(PeerPointers in, PeerPointers out, int n_ranks, int64_t begin, int64_t end) {
+  // [begin, end) in units of V (16 bytes)
+  for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    V acc = reinterpret_cast<const V*>(in.p[0])[i];
+    T* a = reinterpret_cast<T*>(&acc);
+#pragma unroll 4
+    for (int p = 1; p < n_ranks; ++p) {
+      const V v = reinterpret_cast<const V*>(in.p[p])[i];
+      const T* b = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) a[e] += b[e];
+    }
+    for (int p = 0; p < n_ranks; ++p) reinterpret_cast<V*>(out.p[p])[i] = acc;
+  }
+}
+
 }  // namespace tpme
 
 using namespace tpme;
@@ -285,6 +310,42 @@ extern "C" int tpme_peer_barrier(void* const* flags_host, int n_ranks, int rank,
   const unsigned long long ns = (unsigned long long)(timeout_seconds * 1e9);
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n_ranks, rank, (unsigned*)epoch, ns,
                                                           (int*)error_flag);
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// all-reduce (sum) of `n` reals held in peer-mapped regions: `in_host[p]` / `out_host[p]` are rank
+// p's input / output regions as mapped in this process (16-byte aligned, padded to a multiple of
+// 16 bytes * n_ranks).  Call between two tpme_peer_barrier calls.
+extern "C" int tpme_peer_allreduce(int dtype, void* const* in_host, void* const* out_host, int n_ranks,
+                                   int rank, int64_t n, void* stream) {
+  TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 or 1");
+  TPME_REQUIRE(n_ranks > 0 && n_ranks <= TPME_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank layout");
+  TPME_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return 0;
+  PeerPointers in, out;
+  memset(&in, 0, sizeof(in));
+  memset(&out, 0, sizeof(out));
+  for (int p = 0; p < n_ranks; ++p) {
+    TPME_REQUIRE(in_host[p] != nullptr && out_host[p] != nullptr, "null peer region");
+    TPME_REQUIRE(((uintptr_t)in_host[p] % 16) == 0 && ((uintptr_t)out_host[p] % 16) == 0, "regions must be 16-byte aligned");
+    in.p[p] = in_host[p];
+    out.p[p] = out_host[p];
+  }
+  const int vec = dtype == 0 ? 4 : 2;
+  const int64_t words = (n + vec - 1) / vec;               // the regions are padded, see above
+  const int64_t per = (words + n_ranks - 1) / n_ranks;
+  const int64_t begin = per * rank < words ? per * rank : words;
+  const int64_t end = begin + per < words ? begin + per : words;
+  if (end <= begin) return 0;
+  int64_t grid = (end - begin + 255) / 256;
+  const int64_t cap = 4ll * num_sms();
+  if (grid > cap) grid = cap;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == 0)
+    peer_allreduce_kernel<float4, float, 4><<<(unsigned)grid, 256, 0, s>>>(in, out, n_ranks, begin, end);
+  else
+    peer_allreduce_kernel<double2, double, 2><<<(unsigned)grid, 256, 0, s>>>(in, out, n_ranks, begin, end);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }

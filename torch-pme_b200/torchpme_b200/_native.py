@@ -107,6 +107,7 @@ SIGNATURES = {
     "tpme_peer_buffer_close": ([_vp], _i),
     "tpme_peer_buffer_destroy": ([_vp], _i),
     "tpme_peer_barrier": ([ctypes.POINTER(_vp), _i, _i, _vp, ctypes.c_double, _vp, _vp], _i),
+    "tpme_peer_allreduce": ([_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i64, _vp], _i),
     "tpme_fft_plan_create": ([ctypes.POINTER(_vp), _i, _i, _i, _i, _i], _i),
     "tpme_fft_plan_destroy": ([_vp], _i),
     "tpme_fft_plan_uses_own_fft": ([_vp], _i),
@@ -552,6 +553,18 @@ def peer_barrier(flag_ptrs, rank: int, epoch, error_flag, timeout_seconds: float
     with _on(epoch, "epoch"):
         _check(lib.tpme_peer_barrier(arr, n, rank, _dev(epoch, "epoch"), float(timeout_seconds),
                                      _dev(error_flag, "error_flag"), _stream()), "tpme_peer_barrier")
+    _count()
+
+
+def peer_allreduce(dtype, device, in_ptrs, out_ptrs, rank: int, n: int):
+    """sum all-reduce of n reals between peer-mapped regions (call between two peer barriers)"""
+    lib = load()
+    w = len(in_ptrs)
+    a = (_vp * w)(*[int(p) for p in in_ptrs])
+    b = (_vp * w)(*[int(p) for p in out_ptrs])
+    with torch.cuda.device(device):
+        _check(lib.tpme_peer_allreduce(0 if dtype == torch.float32 else 1, a, b, w, rank, n, _stream()),
+               "tpme_peer_allreduce")
     _count()
 
 

@@ -203,6 +203,68 @@ class PeerExchange:
         return self.hat
 
 
+class TorchReducer:
+    """partial results summed with ``torch.distributed.all_reduce`` (NCCL, or gloo in the CPU tests)"""
+
+    def __init__(self, group, world):
+        self.group, self.world = group, world
+
+    def zeros(self, n: int, dtype, device) -> torch.Tensor:
+        return torch.zeros(n, dtype=dtype, device=device)
+
+    def all_reduce(self, flat: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(flat, group=self.group)
+        return flat
+
+
+class PeerReducer:
+    """
+    Sum all-reduce over NVLink peer memory (``tpme_peer_allreduce``): the kernels accumulate their
+    partial results straight into this rank's input region; after a flag barrier every rank pulls
+    its slice from all peers, sums and pushes the result to all output regions.  One kernel and two
+    barriers instead of a ring all-reduce (2 (W - 1) latency-bound steps at these sizes).
+    """
+
+    _FLAG_BYTES = 256
+
+    def __init__(self, n_max: int, dtype, device, group, world: int, rank: int):
+        self.world, self.rank, self.dtype, self.device = world, rank, dtype, device
+        esize = 4 if dtype == torch.float32 else 8
+        self.n_max = n_max
+        region = (n_max * esize + 16 * world + 255) // 256 * 256
+        self._off_in, self._off_out = self._FLAG_BYTES, self._FLAG_BYTES + region
+        self.buffer = _native.PeerBuffer(self._FLAG_BYTES + 2 * region, device)
+        mine = torch.tensor(list(self.buffer.handle), dtype=torch.uint8, device=device)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=group)
+        self.peer_base = [self.buffer.ptr if p == rank else self.buffer.open_peer(bytes(handles[p].cpu().tolist()))
+                          for p in range(world)]
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        self._in = self.buffer.as_tensor(self._off_in, (n_max,), dtype)
+        self._out = self.buffer.as_tensor(self._off_out, (n_max,), dtype)
+        dist.barrier(group=group)
+
+    def zeros(self, n: int, dtype, device) -> torch.Tensor:
+        assert n <= self.n_max and dtype == self.dtype
+        return self._in[:n].zero_()
+
+    def all_reduce(self, flat: torch.Tensor) -> torch.Tensor:
+        """`flat` is the view handed out by :meth:`zeros`; returns a fresh tensor with the sums"""
+        n = flat.numel()
+        _native.peer_barrier(self.peer_base, self.rank, self.epoch, self.error)
+        _native.peer_allreduce(self.dtype, self.device, [b + self._off_in for b in self.peer_base],
+                               [b + self._off_out for b in self.peer_base], self.rank, n)
+        _native.peer_barrier(self.peer_base, self.rank, self.epoch, self.error)
+        return self._out[:n].clone()
+
+    def check(self):
+        code = int(self.error.item())
+        if code:
+            raise RuntimeError(f"peer barrier timed out waiting for rank {code - 1}")
+
+
 class SlabFilter:
     """``irfft3(G * rfft3(.))`` of a mesh distributed as x slabs (buffers reused across calls)."""
 
@@ -237,7 +299,8 @@ class SlabFilter:
 
 class _SlabStepConfig:
     __slots__ = ("r2u", "ns", "nodes", "method", "green_args", "pair_pot", "full_list", "half_ivolume",
-                 "self_half", "background_ivolume", "layout", "filter", "group", "ops", "shard_pairs")
+                 "self_half", "background_ivolume", "layout", "filter", "group", "ops", "shard_pairs",
+                 "reducer", "n_atoms")
 
 
 class _SlabMeshPotential(torch.autograd.Function):
@@ -257,7 +320,7 @@ class _SlabMeshPotential(torch.autograd.Function):
         idx = neighbor_indices[lo:hi].contiguous()
         d = distances.detach()[lo:hi].contiguous()
         mask = None if mask_u8 is None else mask_u8[lo:hi].contiguous()
-        out = torch.zeros_like(q)
+        out = cfg.reducer.zeros(q.numel(), q.dtype, q.device).view(q.shape)
         cuda = q.is_cuda
         if cuda:
             main = torch.cuda.current_stream()
@@ -278,8 +341,7 @@ class _SlabMeshPotential(torch.autograd.Function):
         epi = ops.make_epilogue(q, zero_dc, cfg.half_ivolume, 0.0, 0.0)
         _, dvalues = ops.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=need_pos,
                                 values_out=out, epilogue=epi, slab=(lay.x0, lay.ns[0]))
-        if lay.world > 1:
-            dist.all_reduce(out, group=cfg.group)
+        out = cfg.reducer.all_reduce(out.view(-1)).view(q.shape)
         out = out - q * cfg.self_half - cfg.background_ivolume * q.sum(dim=0)
         ctx.cfg, ctx.pair_range, ctx.n_pairs = cfg, (lo, hi), n_pairs
         ctx.save_for_backward(q, pos, d, idx, mask, dvalues)
@@ -294,10 +356,10 @@ class _SlabMeshPotential(torch.autograd.Function):
         need_q, need_pos, need_d = ctx.needs_input_grad[:3]
         g = grad_out.contiguous()
         n, c = q.shape
-        # one flat buffer so that a single all-reduce returns dL/dpositions and dL/dcharges
-        flat = torch.zeros(n * (3 + c), dtype=q.dtype, device=q.device)
+        # one flat buffer so that a single all-reduce returns dL/dpositions (and dL/dcharges)
+        flat = cfg.reducer.zeros(n * (3 + c) if need_q else 3 * n, q.dtype, q.device)
         g_pos = flat[: 3 * n].view(n, 3)
-        g_q = flat[3 * n:].view(n, c)
+        g_q = flat[3 * n:].view(n, c) if need_q else None
         g_d = None
         cuda = q.is_cuda
         forked = False
@@ -339,9 +401,10 @@ class _SlabMeshPotential(torch.autograd.Function):
                 ops.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi, slab=slab)
         if forked:
             torch.cuda.current_stream().wait_stream(_side_stream(q.device))
-        if lay.world > 1:
-            dist.all_reduce(flat, group=cfg.group)
+        flat = cfg.reducer.all_reduce(flat)
+        g_pos = flat[: 3 * n].view(n, 3)
         if need_q:
+            g_q = flat[3 * n:].view(n, c)
             g_q = g_q - g * cfg.self_half - cfg.background_ivolume * g.sum(dim=0)
         return (g_q if need_q else None), (g_pos if need_pos else None), g_d, None, None, None
 
@@ -397,7 +460,7 @@ class _SlabMixin:
         # CUDA graph) must find the same exchange buffers again
         key = (geom.cell.tobytes(), ns, kind, exponent, smearing, prefactor, pot.exclusion_radius,
                pot.exclusion_degree, self.full_neighbor_list, world, rank, n_channels, charges.dtype,
-               charges.device)
+               charges.device, charges.shape[0])
         cfg = self._slab_cfgs.get(key)
         if cfg is None:
             ops = self._ops
@@ -418,6 +481,12 @@ class _SlabMixin:
             cfg.background_ivolume = float(pot.background_correction()) * ivolume
             cfg.filter = SlabFilter(cfg.layout, n_channels, charges.dtype, charges.device,
                                     self.process_group, self.transport, ops)
+            cfg.n_atoms = charges.shape[0]
+            if self.transport.startswith("p2p") and world > 1:
+                cfg.reducer = PeerReducer(cfg.n_atoms * (3 + n_channels), charges.dtype, charges.device,
+                                          self.process_group, world, rank)
+            else:
+                cfg.reducer = TorchReducer(self.process_group, world)
             if len(self._slab_cfgs) >= 4:   # a captured graph keeps its own reference (GraphedStep)
                 self._slab_cfgs.pop(next(iter(self._slab_cfgs)))
             self._slab_cfgs[key] = cfg
