@@ -83,16 +83,27 @@ int tpme_gather_vjp(int dtype, const void* mesh, const void* positions, const vo
  * part).  x0 = 0, nx_local = nx is exactly the plain call. */
 int tpme_spread_slab(int dtype, const void* positions, const void* weights, int64_t n_points,
                      int n_channels, const double* r2u_host, int nx, int ny, int nz, int x0,
-                     int nx_local, int nodes, int method, void* mesh, int accumulate, void* stream);
+                     int nx_local, const int* point_list, const int* list_count, int nodes,
+                     int method, void* mesh, int accumulate, void* stream);
 int tpme_gather_slab(int dtype, const void* mesh, const void* positions, int64_t n_points,
                      int n_channels, const double* r2u_host, int nx, int ny, int nz, int x0,
-                     int nx_local, int nodes, int method, void* values, void* dvalues,
-                     const tpme_point_epilogue* epilogue, void* stream);
+                     int nx_local, const int* point_list, const int* list_count, int nodes,
+                     int method, void* values, void* dvalues, const tpme_point_epilogue* epilogue,
+                     void* stream);
 int tpme_gather_vjp_slab(int dtype, const void* mesh, const void* positions, const void* coef,
                          int64_t n_points, int n_channels, const double* r2u_host, int nx, int ny,
-                         int nz, int x0, int nx_local, int nodes, int method, void* grad_positions,
+                         int nz, int x0, int nx_local, const int* point_list,
+                         const int* list_count, int nodes, int method, void* grad_positions,
                          void* values, int accumulate, void* grad_r2u,
                          const tpme_point_epilogue* epilogue, void* stream);
+/* `point_list` / `list_count` (device, may both be NULL = all points): the indices of the points
+ * whose stencil reaches into the slab and their number, as written by
+ * tpme_slab_select_points (capacity n_points ints + 1 int).  With a list the kernels stride over
+ * it -- a rank of a W-GPU run touches ~1/W of the atoms -- and leave the outputs of all other
+ * points untouched (gathers into zero-initialised / accumulated outputs). */
+int tpme_slab_select_points(int dtype, const void* positions, int64_t n_points,
+                            const double* r2u_host, int nx, int ny, int nz, int x0, int nx_local,
+                            int nodes, int* point_list, int* list_count, void* stream);
 
 /* ---- reciprocal space ---------------------------------------------------------------
  * replaces KSpaceFilter.update + forward and P3MKSpaceFilter

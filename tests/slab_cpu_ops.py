@@ -50,7 +50,12 @@ class CpuOps:
 
     # ---- mesh interpolation -----------------------------------------------------------------
     @staticmethod
-    def spread(positions, weights, r2u, ns, nodes, method, out=None, slab=None):
+    def slab_select_points(positions, r2u, ns, nodes, slab):
+        """the emulation visits every point (foreign points contribute exact zeros)"""
+        return None
+
+    @staticmethod
+    def spread(positions, weights, r2u, ns, nodes, method, out=None, slab=None, point_list=None):
         cell = _cell_from_r2u(r2u, ns)
         full = oracle.points_to_mesh(_np(weights), _np(positions), cell, ns, nodes, _METHOD[method])
         x0, nxl = (0, ns[0]) if slab is None else slab
@@ -68,7 +73,7 @@ class CpuOps:
 
     @classmethod
     def gather(cls, mesh, positions, r2u, nodes, method, want_values=True, want_grad=False, values_out=None,
-               epilogue=None, slab=None):
+               epilogue=None, slab=None, point_list=None):
         vals, dvals = cls._gather_parts(mesh, positions, r2u, nodes, method, slab)
         vals_t = torch.from_numpy(vals).to(mesh.dtype)
         if epilogue is not None:
@@ -83,7 +88,7 @@ class CpuOps:
 
     @classmethod
     def gather_vjp(cls, mesh, positions, coef, r2u, nodes, method, grad_positions=None, want_values=False,
-                   want_grad_r2u=False, values_out=None, epilogue=None, slab=None):
+                   want_grad_r2u=False, values_out=None, epilogue=None, slab=None, point_list=None):
         vals, dvals = cls._gather_parts(mesh, positions, r2u, nodes, method, slab)
         vals_t = torch.from_numpy(vals).to(mesh.dtype)
         g = torch.einsum("ic,icd->id", coef.double(), torch.from_numpy(dvals))

@@ -61,6 +61,15 @@ def test_virtual_ranks_reproduce_single_gpu(method, nodes, channels, ns, world, 
     rho_full = _native.spread(pos, w, r2u, ns, nodes, mid)
     rho = [_native.spread(pos, w, r2u, ns, nodes, mid, slab=(lay.x0, lay.nxl)) for lay in layouts]
     assert rel_err(torch.cat(rho, dim=1), rho_full) < tol
+    # the same through the per-slab point lists (only the atoms that reach into the slab are visited)
+    plists = [_native.slab_select_points(pos, r2u, ns, nodes, (lay.x0, lay.nxl)) for lay in layouts]
+    rho_l = [_native.spread(pos, w, r2u, ns, nodes, mid, slab=(lay.x0, lay.nxl), point_list=pl)
+             for lay, pl in zip(layouts, plists)]
+    assert rel_err(torch.cat(rho_l, dim=1), rho_full) < tol
+    counts = [int(pl[1]) for pl in plists]
+    assert all(0 < c <= n for c in counts) and sum(counts) >= n
+    if nx >= 4 * nodes * world:
+        assert sum(counts) < 2 * n
 
     # ---- filter through W virtual ranks (the peer-exchange data path on one device)
     green = _native.make_green(_native.GREEN_COULOMB, 0.41, geom.recip, geom.spacing(ns), smearing=1.3,
@@ -111,6 +120,18 @@ def test_virtual_ranks_reproduce_single_gpu(method, nodes, channels, ns, world, 
     for r, lay in enumerate(layouts):
         v, dv = _native.gather(phi[r], pos, r2u, nodes, mid, want_grad=True, slab=(lay.x0, nx))
         gp, _, _ = _native.gather_vjp(phi[r], pos, w, r2u, nodes, mid, slab=(lay.x0, nx))
+        # list mode leaves foreign points untouched: start from zeros / accumulate
+        v_l = torch.zeros_like(v)
+        dv_l = torch.zeros_like(dv)
+        gp_l = torch.zeros_like(gp)
+        lst, cnt = plists[r]
+        sel = lst[: int(cnt)].long()
+        _, dv_tmp = _native.gather(phi[r], pos, r2u, nodes, mid, want_grad=True, values_out=v_l, slab=(lay.x0, nx),
+                                   point_list=plists[r])
+        dv_l[sel] = dv_tmp[sel]
+        _native.gather_vjp(phi[r], pos, w, r2u, nodes, mid, grad_positions=gp_l, slab=(lay.x0, nx),
+                           point_list=plists[r])
+        assert rel_err(v_l, v) < tol and rel_err(gp_l, gp) < tol * 10 and rel_err(dv_l, dv) < tol * 10
         v_sum, dv_sum, gp_sum = v_sum + v, dv_sum + dv, gp_sum + gp
     assert rel_err(v_sum, v_full) < tol
     if nodes > 1:

@@ -58,17 +58,7 @@ __device__ __forceinline__ void point_stencil(const T* __restrict__ pos, const M
   }
 }
 
-// first stencil node of one axis only, and whether the N planes starting there reach into the
-// local x slab [x0, x0 + nxl): lets slab-decomposed kernels drop foreign points before any
-// weight is evaluated
-template <typename T, int N>
-__device__ __forceinline__ int axis_first(const T* __restrict__ pos, const Mat3<T>& r2u,
-                                          const MeshDims<T>& dims, int a) {
-  const T u = pos[0] * r2u.m[a] + pos[1] * r2u.m[3 + a] + pos[2] * r2u.m[6 + a];
-  const T base = (N % 2 == 0) ? floor_t(u) : rint_t(u);
-  return wrap_base<T>(base + T(1 - (N + 1) / 2), dims.n[a], dims.inv_n[a]);
-}
-
+// do the `nodes` planes starting at `first` reach into the x slab [x0, x0 + nxl) of an nx-periodic axis?
 __device__ __forceinline__ bool touches_slab(int first, int nodes, int nx, int x0, int nxl) {
   int ahead = first - x0;      // (first - x0) mod nx < nxl: the first plane lies inside
   if (ahead < 0) ahead += nx;
@@ -102,15 +92,17 @@ template <int N> struct GroupSize {
 template <typename T, int METHOD, int N>
 __global__ void __launch_bounds__(256)
 spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, int64_t n_points,
-              int n_channels, Mat3<T> r2u, MeshDims<T> dims, int x0, int nxl, T* __restrict__ mesh) {
+              int n_channels, Mat3<T> r2u, MeshDims<T> dims, int x0, int nxl, T* __restrict__ mesh,
+              const int* __restrict__ point_list, const int* __restrict__ list_count) {
   constexpr int G = GroupSize<N>::value;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t point = tid / G;
-  if (point >= n_points) return;
-  const int c = (int)(tid - point * G);
-  if (c >= N) return;
+  const int64_t total = point_list != nullptr ? (int64_t)*list_count : n_points;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid / G < total; tid += stride) {
+  const int64_t entry = tid / G;
+  const int c = (int)(tid - entry * G);
+  if (c >= N) continue;
+  const int64_t point = point_list != nullptr ? (int64_t)point_list[entry] : entry;
   const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
-  if (nxl < nx && !touches_slab(axis_first<T, N>(positions + 3 * point, r2u, dims, 0), N, nx, x0, nxl)) return;
 
   int first[3];
   T w[3][N], dw[3][N];
@@ -142,6 +134,34 @@ spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, in
       for (int b = 0; b < N; ++b) red_add(dst + (xoff[a] + yoff[b]), qa * w[1][b]);
     }
   }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// slab decomposition: list of the points whose stencil reaches into the x slab [x0, x0 + nxl)
+// (warp-aggregated append; the order inside the list is irrelevant to the results)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+select_slab_points_kernel(const T* __restrict__ positions, int64_t n_points, Mat3<T> r2u,
+                          MeshDims<T> dims, int nodes, int x0, int nxl, int* __restrict__ list,
+                          int* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (i < n_points) {
+    const T* pos = positions + 3 * i;
+    const T u = pos[0] * r2u.m[0] + pos[1] * r2u.m[3] + pos[2] * r2u.m[6];
+    const T base = (nodes % 2 == 0) ? floor_t(u) : rint_t(u);
+    const int first = wrap_base<T>(base + T(1 - (nodes + 1) / 2), dims.n[0], dims.inv_n[0]);
+    keep = touches_slab(first, nodes, dims.n[0], x0, nxl);
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+  if (ballot == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base_slot = 0;
+  if (lane == 0) base_slot = atomicAdd(count, __popc(ballot));
+  base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
+  if (keep) list[base_slot + __popc(ballot & ((1u << lane) - 1))] = (int)i;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -349,42 +369,50 @@ gather_point_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
                     const T* __restrict__ coef, int64_t n_points, int n_channels, Mat3<T> r2u,
                     MeshDims<T> dims, int x0, int nxl, T* __restrict__ values, T* __restrict__ dvalues,
                     T* __restrict__ grad_positions, int accumulate, T* __restrict__ grad_r2u,
-                    PointEpilogue<T> epi) {
+                    PointEpilogue<T> epi, const int* __restrict__ point_list,
+                    const int* __restrict__ list_count) {
   constexpr int VEC = Vec16<T>::VEC;
   constexpr int NV = (N + VEC - 2) / VEC + 1;     // vectors covering any window of N starting at o < VEC
   constexpr int W = NV * VEC;
   constexpr bool DERIV = (MODE & 6) != 0;
-  const int64_t point_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = point_raw < n_points;
+  // with a point list (slab decomposition: the points whose stencil reaches into the local slab)
+  // the threads stride over the list, whose length is only known on the device
+  const int64_t total = point_list != nullptr ? (int64_t)*list_count : n_points;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  do {
+  const bool valid = it < total;
   if (!valid && !((MODE & 4) && grad_r2u != nullptr)) return;
-  const int64_t point = valid ? point_raw : n_points - 1;
+  const int64_t point = valid ? (point_list != nullptr ? (int64_t)point_list[it] : it) : n_points - 1;
 
+  int first[3];
+  T w[3][N], dw[3][N];
+  point_stencil<T, METHOD, N, DERIV>(positions + 3 * point, r2u, dims, first, w, dw);
   const int nx = dims.n[0], ny = dims.n[1], nz = dims.n[2];
   const unsigned plane = (unsigned)ny * nz;
   const int64_t mesh_size = (int64_t)plane * nxl;
-  int first[3];
-  T w[3][N], dw[3][N];
   unsigned xoff[N], yoff[N];
-  unsigned zoff[NV];
-  T wz[W], dwz[W];
-  bool any_inside = nxl >= nx ||
-                    touches_slab(axis_first<T, N>(positions + 3 * point, r2u, dims, 0), N, nx, x0, nxl);
-  if (any_inside) {
-    point_stencil<T, METHOD, N, DERIV>(positions + 3 * point, r2u, dims, first, w, dw);
+  bool any_inside = false;
+  {
     int ix = first[0], iy = first[1];
 #pragma unroll
     for (int a = 0; a < N; ++a) {
       const unsigned lx = (unsigned)(ix - x0);
       const bool inside = lx < (unsigned)nxl;
+      any_inside |= inside;
       xoff[a] = inside ? lx * plane : 0u;
       if (!inside) { w[0][a] = T(0); if (DERIV) dw[0][a] = T(0); }
       yoff[a] = (unsigned)iy * nz;
       ix = (ix + 1 >= nx) ? wrap_add(ix + 1, nx) : ix + 1;
       iy = (iy + 1 >= ny) ? wrap_add(iy + 1, ny) : iy + 1;
     }
-    // z window: aligned vectors, weights shifted by o = first[2] mod VEC
-    const int zb = first[2] & ~(VEC - 1);
-    const int o = first[2] - zb;
+  }
+  // z window: aligned vectors, weights shifted by o = first[2] mod VEC
+  const int zb = first[2] & ~(VEC - 1);
+  const int o = first[2] - zb;
+  unsigned zoff[NV];
+  T wz[W], dwz[W];
+  {
     int z = zb;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -498,6 +526,8 @@ gather_point_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
       }
     }
   }
+  it += stride;
+  } while (point_list != nullptr && it < total);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -511,27 +541,38 @@ static MeshDims<T> make_dims(int nx, int ny, int nz) {
   return d;
 }
 
+// local x slab of a decomposed mesh (x0 = 0, nxl = nx: the whole mesh) and, optionally, the device
+// list of the points that reach into it
+struct SlabArgs {
+  int x0, nxl;
+  const int* list;
+  const int* count;
+};
+
 template <typename T, int METHOD, int N>
 int launch_spread(const void* positions, const void* weights, int64_t n_points, int n_channels,
-                  const double* r2u, int nx, int ny, int nz, int x0, int nxl, void* mesh,
+                  const double* r2u, int nx, int ny, int nz, SlabArgs sl, void* mesh,
                   cudaStream_t stream) {
   const int64_t threads = n_points * GroupSize<N>::value;  // one lane per (point, z offset)
   const int block = 256;
-  const int64_t grid = (threads + block - 1) / block;
+  int64_t grid = (threads + block - 1) / block;
   if (grid == 0) return 0;
+  // list mode: the list length lives on the device, the threads stride over it
+  if (sl.list != nullptr && grid > 8ll * num_sms()) grid = 8ll * num_sms();
   spread_kernel<T, METHOD, N><<<(unsigned)grid, block, 0, stream>>>(
       (const T*)positions, (const T*)weights, n_points, n_channels, load_mat3<T>(r2u),
-      make_dims<T>(nx, ny, nz), x0, nxl, (T*)mesh);
+      make_dims<T>(nx, ny, nz), sl.x0, sl.nxl, (T*)mesh, sl.list, sl.count);
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <typename T, int METHOD, int N, int MODE>
 int launch_gather(const void* mesh, const void* positions, const void* coef, int64_t n_points,
-                  int n_channels, const double* r2u, int nx, int ny, int nz, int x0, int nxl,
+                  int n_channels, const double* r2u, int nx, int ny, int nz, SlabArgs sl,
                   void* values, void* dvalues, void* grad_positions, int accumulate, void* grad_r2u,
                   const tpme_point_epilogue* epi_host, cudaStream_t stream) {
   constexpr int G = GroupSize<N>::value;
+  const int x0 = sl.x0, nxl = sl.nxl;
   PointEpilogue<T> epi;
   epi.enabled = epi_host != nullptr;
   if (epi_host) {
@@ -550,14 +591,19 @@ int launch_gather(const void* mesh, const void* positions, const void* coef, int
   static const bool force_lanes = [] { const char* e = getenv("TPME_GATHER"); return e && e[0] == 'l'; }();
   if (!force_lanes && nz % Vec16<T>::VEC == 0 && ((uintptr_t)mesh % 16) == 0) {
     const int block = n_points >= 4 * 128 * (int64_t)num_sms() ? 128 : 64;
-    const int64_t grid = (n_points + block - 1) / block;
+    int64_t grid = (n_points + block - 1) / block;
+    if (sl.list != nullptr) {
+      TPME_REQUIRE(grad_r2u == nullptr, "cell gradients are not available with a point list");
+      if (grid > 8ll * num_sms()) grid = 8ll * num_sms();
+    }
     gather_point_kernel<T, METHOD, N, MODE><<<(unsigned)grid, block, 0, stream>>>(
         (const T*)mesh, (const T*)positions, (const T*)coef, n_points, n_channels,
         load_mat3<T>(r2u), make_dims<T>(nx, ny, nz), x0, nxl, (T*)values, (T*)dvalues, (T*)grad_positions,
-        accumulate, (T*)grad_r2u, epi);
+        accumulate, (T*)grad_r2u, epi, sl.list, sl.count);
     TPME_CUDA_OK(cudaGetLastError());
     return 0;
   }
+  TPME_REQUIRE(sl.list == nullptr, "point lists need mesh rows of whole 16-byte vectors (nz % 4 == 0)");
   const int64_t threads = n_points * G;
   const int block = 256;
   const int64_t grid = (threads + block - 1) / block;
@@ -592,23 +638,23 @@ int launch_gather(const void* mesh, const void* positions, const void* coef, int
 
 template <typename T>
 int spread_dispatch(const void* positions, const void* weights, int64_t n_points, int n_channels,
-                    const double* r2u, int nx, int ny, int nz, int x0, int nxl, int nodes, int method,
+                    const double* r2u, int nx, int ny, int nz, SlabArgs sl, int nodes, int method,
                     void* mesh, cudaStream_t stream) {
 #define CALL(M, N) \
-  launch_spread<T, M, N>(positions, weights, n_points, n_channels, r2u, nx, ny, nz, x0, nxl, mesh, stream)
+  launch_spread<T, M, N>(positions, weights, n_points, n_channels, r2u, nx, ny, nz, sl, mesh, stream)
   TPME_DISPATCH_STENCIL(CALL)
 #undef CALL
 }
 
 template <typename T, int MODE>
 int gather_dispatch(const void* mesh, const void* positions, const void* coef, int64_t n_points,
-                    int n_channels, const double* r2u, int nx, int ny, int nz, int x0, int nxl,
+                    int n_channels, const double* r2u, int nx, int ny, int nz, SlabArgs sl,
                     int nodes, int method, void* values, void* dvalues, void* grad_positions,
                     int accumulate, void* grad_r2u, const tpme_point_epilogue* epi,
                     cudaStream_t stream) {
 #define CALL(M, N)                                                                                 \
-  launch_gather<T, M, N, MODE>(mesh, positions, coef, n_points, n_channels, r2u, nx, ny, nz, x0,  \
-                               nxl, values, dvalues, grad_positions, accumulate, grad_r2u, epi, stream)
+  launch_gather<T, M, N, MODE>(mesh, positions, coef, n_points, n_channels, r2u, nx, ny, nz, sl,  \
+                               values, dvalues, grad_positions, accumulate, grad_r2u, epi, stream)
   TPME_DISPATCH_STENCIL(CALL)
 #undef CALL
 }
@@ -631,10 +677,13 @@ static int check_slab(int nx, int x0, int nxl) {
 
 extern "C" int tpme_spread_slab(int dtype, const void* positions, const void* weights,
                                 int64_t n_points, int n_channels, const double* r2u_host, int nx,
-                                int ny, int nz, int x0, int nx_local, int nodes, int method,
-                                void* mesh, int accumulate, void* stream) {
+                                int ny, int nz, int x0, int nx_local, const int* point_list,
+                                const int* list_count, int nodes, int method, void* mesh,
+                                int accumulate, void* stream) {
   if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
   if (int rc = check_slab(nx, x0, nx_local)) return rc;
+  TPME_REQUIRE((point_list == nullptr) == (list_count == nullptr), "point_list and list_count go together");
+  const SlabArgs sl{x0, nx_local, point_list, list_count};
   cudaStream_t s = (cudaStream_t)stream;
   const size_t elem = dtype == 0 ? 4 : 8;
   if (!accumulate)
@@ -642,9 +691,9 @@ extern "C" int tpme_spread_slab(int dtype, const void* positions, const void* we
   if (n_points == 0 || n_channels == 0) return 0;
   if (dtype == 0)
     return spread_dispatch<float>(positions, weights, n_points, n_channels, r2u_host, nx, ny, nz,
-                                  x0, nx_local, nodes, method, mesh, s);
+                                  sl, nodes, method, mesh, s);
   return spread_dispatch<double>(positions, weights, n_points, n_channels, r2u_host, nx, ny, nz,
-                                 x0, nx_local, nodes, method, mesh, s);
+                                 sl, nodes, method, mesh, s);
 }
 
 extern "C" int tpme_spread(int dtype, const void* positions, const void* weights,
@@ -652,23 +701,25 @@ extern "C" int tpme_spread(int dtype, const void* positions, const void* weights
                            int ny, int nz, int nodes, int method, void* mesh, int accumulate,
                            void* stream) {
   return tpme_spread_slab(dtype, positions, weights, n_points, n_channels, r2u_host, nx, ny, nz, 0,
-                          nx, nodes, method, mesh, accumulate, stream);
+                          nx, nullptr, nullptr, nodes, method, mesh, accumulate, stream);
 }
 
 extern "C" int tpme_gather_slab(int dtype, const void* mesh, const void* positions,
                                 int64_t n_points, int n_channels, const double* r2u_host, int nx,
-                                int ny, int nz, int x0, int nx_local, int nodes, int method,
-                                void* values, void* dvalues, const tpme_point_epilogue* epilogue,
-                                void* stream) {
+                                int ny, int nz, int x0, int nx_local, const int* point_list,
+                                const int* list_count, int nodes, int method, void* values,
+                                void* dvalues, const tpme_point_epilogue* epilogue, void* stream) {
   if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
   if (int rc = check_slab(nx, x0, nx_local)) return rc;
+  TPME_REQUIRE((point_list == nullptr) == (list_count == nullptr), "point_list and list_count go together");
+  const SlabArgs sl{x0, nx_local, point_list, list_count};
   TPME_REQUIRE(values != nullptr || dvalues != nullptr, "nothing to compute");
   if (n_points == 0 || n_channels == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const int mode = (values ? 1 : 0) | (dvalues ? 2 : 0);
 #define GO(T, MODE)                                                                          \
   return gather_dispatch<T, MODE>(mesh, positions, nullptr, n_points, n_channels, r2u_host,  \
-                                  nx, ny, nz, x0, nx_local, nodes, method, values, dvalues,  \
+                                  nx, ny, nz, sl, nodes, method, values, dvalues,            \
                                   nullptr, 0, nullptr, epilogue, s)
   if (dtype == 0) {
     if (mode == 1) GO(float, 1);
@@ -686,17 +737,20 @@ extern "C" int tpme_gather(int dtype, const void* mesh, const void* positions, i
                            int nodes, int method, void* values, void* dvalues,
                            const tpme_point_epilogue* epilogue, void* stream) {
   return tpme_gather_slab(dtype, mesh, positions, n_points, n_channels, r2u_host, nx, ny, nz, 0, nx,
-                          nodes, method, values, dvalues, epilogue, stream);
+                          nullptr, nullptr, nodes, method, values, dvalues, epilogue, stream);
 }
 
 extern "C" int tpme_gather_vjp_slab(int dtype, const void* mesh, const void* positions,
                                     const void* coef, int64_t n_points, int n_channels,
                                     const double* r2u_host, int nx, int ny, int nz, int x0,
-                                    int nx_local, int nodes, int method, void* grad_positions,
-                                    void* values, int accumulate, void* grad_r2u,
+                                    int nx_local, const int* point_list, const int* list_count,
+                                    int nodes, int method, void* grad_positions, void* values,
+                                    int accumulate, void* grad_r2u,
                                     const tpme_point_epilogue* epilogue, void* stream) {
   if (int rc = check_mesh_args(dtype, nx, ny, nz, n_channels, n_points)) return rc;
   if (int rc = check_slab(nx, x0, nx_local)) return rc;
+  TPME_REQUIRE((point_list == nullptr) == (list_count == nullptr), "point_list and list_count go together");
+  const SlabArgs sl{x0, nx_local, point_list, list_count};
   TPME_REQUIRE(grad_positions != nullptr && coef != nullptr, "grad_positions / coef missing");
   if (n_points == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
@@ -707,7 +761,7 @@ extern "C" int tpme_gather_vjp_slab(int dtype, const void* mesh, const void* pos
   }
 #define GO(T, MODE)                                                                           \
   return gather_dispatch<T, MODE>(mesh, positions, coef, n_points, n_channels, r2u_host, nx,  \
-                                  ny, nz, x0, nx_local, nodes, method, values, nullptr,       \
+                                  ny, nz, sl, nodes, method, values, nullptr,                 \
                                   grad_positions, accumulate, grad_r2u, epilogue, s)
   if (dtype == 0) {
     if (values) GO(float, 5);
@@ -725,6 +779,30 @@ extern "C" int tpme_gather_vjp(int dtype, const void* mesh, const void* position
                                void* grad_r2u, const tpme_point_epilogue* epilogue,
                                void* stream) {
   return tpme_gather_vjp_slab(dtype, mesh, positions, coef, n_points, n_channels, r2u_host, nx, ny,
-                              nz, 0, nx, nodes, method, grad_positions, values, accumulate, grad_r2u,
-                              epilogue, stream);
+                              nz, 0, nx, nullptr, nullptr, nodes, method, grad_positions, values,
+                              accumulate, grad_r2u, epilogue, stream);
+}
+
+extern "C" int tpme_slab_select_points(int dtype, const void* positions, int64_t n_points,
+                                       const double* r2u_host, int nx, int ny, int nz, int x0,
+                                       int nx_local, int nodes, int* point_list, int* list_count,
+                                       void* stream) {
+  if (int rc = check_mesh_args(dtype, nx, ny, nz, 1, n_points)) return rc;
+  if (int rc = check_slab(nx, x0, nx_local)) return rc;
+  TPME_REQUIRE(point_list != nullptr && list_count != nullptr, "null output");
+  TPME_REQUIRE(n_points < (1ll << 31), "point lists hold 32-bit indices");
+  cudaStream_t s = (cudaStream_t)stream;
+  TPME_CUDA_OK(cudaMemsetAsync(list_count, 0, sizeof(int), s));
+  if (n_points == 0) return 0;
+  const int64_t grid = (n_points + 255) / 256;
+  if (dtype == 0)
+    select_slab_points_kernel<float><<<(unsigned)grid, 256, 0, s>>>(
+        (const float*)positions, n_points, load_mat3<float>(r2u_host), make_dims<float>(nx, ny, nz), nodes, x0,
+        nx_local, point_list, list_count);
+  else
+    select_slab_points_kernel<double><<<(unsigned)grid, 256, 0, s>>>(
+        (const double*)positions, n_points, load_mat3<double>(r2u_host), make_dims<double>(nx, ny, nz), nodes,
+        x0, nx_local, point_list, list_count);
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
 }

@@ -91,11 +91,12 @@ SIGNATURES = {
                      ctypes.POINTER(_PointEpilogue), _vp], _i),
     "tpme_gather_vjp": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp,
                          ctypes.POINTER(_PointEpilogue), _vp], _i),
-    "tpme_spread_slab": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp], _i),
-    "tpme_gather_slab": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp,
+    "tpme_spread_slab": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp], _i),
+    "tpme_gather_slab": ([_i, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp,
                           ctypes.POINTER(_PointEpilogue), _vp], _i),
-    "tpme_gather_vjp_slab": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i,
-                              _vp, ctypes.POINTER(_PointEpilogue), _vp], _i),
+    "tpme_gather_vjp_slab": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp,
+                              _i, _vp, ctypes.POINTER(_PointEpilogue), _vp], _i),
+    "tpme_slab_select_points": ([_i, _vp, _i64, _dp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "tpme_slab_fft_yz": ([_i, _i, _vp, _vp, _i, _i, _i, _vp], _i),
     "tpme_slab_fft_x_green": ([_i, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
     "tpme_slab_exchange_copy": ([_i, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
@@ -210,8 +211,33 @@ def _count(n=1):
 # --------------------------------------------------------------------------------------
 # mesh interpolation
 # --------------------------------------------------------------------------------------
-def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=None):
-    """`slab` = (x0, nx_local): spread into the local x slab (C, nx_local, ny, nz) only"""
+def _list_args(point_list):
+    if point_list is None:
+        return None, None
+    lst, count = point_list
+    return _dev(lst, "point_list"), _dev(count, "list_count")
+
+
+def slab_select_points(positions, r2u, ns, nodes: int, slab):
+    """(list int32 (N,), count int32 (1,)) of the points whose stencil reaches into `slab` = (x0, nx_local)"""
+    lib = load()
+    n = positions.shape[0]
+    nx, ny, nz = ns
+    lst = torch.empty(max(n, 1), dtype=torch.int32, device=positions.device)
+    count = torch.empty(1, dtype=torch.int32, device=positions.device)
+    with _on(positions, "positions"):
+        _check(lib.tpme_slab_select_points(_dtype_id(positions), _dev(positions, "positions"), n, _mat9(r2u),
+                                           nx, ny, nz, slab[0], slab[1], nodes, _dev(lst, "list"),
+                                           _dev(count, "count"), _stream()), "tpme_slab_select_points")
+    _count()
+    return lst, count
+
+
+def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=None, point_list=None):
+    """
+    `slab` = (x0, nx_local): spread into the local x slab (C, nx_local, ny, nz) only;
+    `point_list` = result of :func:`slab_select_points` for that slab
+    """
     lib = load()
     n, c = weights.shape
     nx, ny, nz = ns
@@ -221,7 +247,8 @@ def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=
     with _on(positions, "positions"):
         _check(lib.tpme_spread_slab(_dtype_id(positions), _dev(positions, "positions"),
                                     _dev(weights, "particle_weights"), n, c, _mat9(r2u), nx, ny, nz,
-                                    x0, nxl, nodes, method, _dev(out, "mesh"), 0, _stream()),
+                                    x0, nxl, *_list_args(point_list), nodes, method, _dev(out, "mesh"), 0,
+                                    _stream()),
                "tpme_spread")
     _count()
     return out
@@ -249,7 +276,7 @@ def _slab_of(mesh, slab):
 
 
 def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want_grad=False,
-           values_out=None, epilogue: _PointEpilogue | None = None, slab=None):
+           values_out=None, epilogue: _PointEpilogue | None = None, slab=None, point_list=None):
     """
     plain gather, or (with `epilogue` and `values_out`) the fused accumulate form.
     `slab` = (x0, nx_global): `mesh` is the local x slab and the results are partial sums.
@@ -263,7 +290,7 @@ def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want
     dvalues = torch.empty((n, c, 3), dtype=mesh.dtype, device=mesh.device) if want_grad else None
     with _on(mesh, "mesh"):
         _check(lib.tpme_gather_slab(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"), n,
-                                    c, _mat9(r2u), nx, ny, nz, x0, nxl, nodes, method,
+                                    c, _mat9(r2u), nx, ny, nz, x0, nxl, *_list_args(point_list), nodes, method,
                                     _dev(values, "values"), _dev(dvalues, "dvalues"),
                                     ctypes.byref(epilogue) if epilogue is not None else None, _stream()),
                "tpme_gather")
@@ -273,7 +300,7 @@ def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want
 
 def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positions=None,
                want_values=False, want_grad_r2u=False, values_out=None,
-               epilogue: _PointEpilogue | None = None, slab=None):
+               epilogue: _PointEpilogue | None = None, slab=None, point_list=None):
     """returns (grad_positions, values | None, grad_r2u (3,3) | None); `slab` as in :func:`gather`"""
     lib = load()
     c, nx, ny, nz, x0, nxl = _slab_of(mesh, slab)
@@ -287,8 +314,9 @@ def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positio
     grad_r2u = torch.zeros((3, 3), dtype=mesh.dtype, device=mesh.device) if want_grad_r2u else None
     with _on(mesh, "mesh"):
         _check(lib.tpme_gather_vjp_slab(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"),
-                                        _dev(coef, "coef"), n, c, _mat9(r2u), nx, ny, nz, x0, nxl, nodes,
-                                        method, _dev(grad_positions, "grad_positions"),
+                                        _dev(coef, "coef"), n, c, _mat9(r2u), nx, ny, nz, x0, nxl,
+                                        *_list_args(point_list), nodes, method,
+                                        _dev(grad_positions, "grad_positions"),
                                         _dev(values, "values"), int(accumulate), _dev(grad_r2u, "grad_r2u"),
                                         ctypes.byref(epilogue) if epilogue is not None else None,
                                         _stream()), "tpme_gather_vjp")

@@ -330,7 +330,10 @@ class _SlabMeshPotential(torch.autograd.Function):
                 ops.pair_forward(q, idx, d, None, mask, cfg.full_list, cfg.pair_pot, out=out)
         else:
             ops.pair_forward(q, idx, d, None, mask, cfg.full_list, cfg.pair_pot, out=out)
-        rho = ops.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, slab=(lay.x0, lay.nxl))
+        # the atoms whose stencil reaches into this rank's slab (~N/W of them): every mesh kernel of
+        # the step strides over this list
+        plist = ops.slab_select_points(pos, cfg.r2u, cfg.ns, cfg.nodes, (lay.x0, lay.nxl)) if lay.world > 1 else None
+        rho = ops.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, slab=(lay.x0, lay.nxl), point_list=plist)
         green = ops.make_green(scale=1.0, **cfg.green_args)
         phi = cfg.filter.apply(rho, green)
         if cuda:
@@ -340,10 +343,10 @@ class _SlabMeshPotential(torch.autograd.Function):
         zero_dc = torch.zeros(q.shape[1], dtype=q.dtype, device=q.device)
         epi = ops.make_epilogue(q, zero_dc, cfg.half_ivolume, 0.0, 0.0)
         _, dvalues = ops.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=need_pos,
-                                values_out=out, epilogue=epi, slab=(lay.x0, lay.ns[0]))
+                                values_out=out, epilogue=epi, slab=(lay.x0, lay.ns[0]), point_list=plist)
         out = cfg.reducer.all_reduce(out.view(-1)).view(q.shape)
         out = out - q * cfg.self_half - cfg.background_ivolume * q.sum(dim=0)
-        ctx.cfg, ctx.pair_range, ctx.n_pairs = cfg, (lo, hi), n_pairs
+        ctx.cfg, ctx.pair_range, ctx.n_pairs, ctx.plist = cfg, (lo, hi), n_pairs, plist
         ctx.save_for_backward(q, pos, d, idx, mask, dvalues)
         return out
 
@@ -383,7 +386,9 @@ class _SlabMeshPotential(torch.autograd.Function):
                                   want_charges=need_q, want_pairs=need_d,
                                   grad_charges_out=g_q if need_q else None, grad_pairs_out=g_d_local)
         if need_q or need_pos:
-            rho_g = ops.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, slab=(lay.x0, lay.nxl))
+            plist = ctx.plist
+            rho_g = ops.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, slab=(lay.x0, lay.nxl),
+                               point_list=plist)
             green = ops.make_green(scale=1.0, **cfg.green_args)
             psi = cfg.filter.apply(rho_g, green)
             if forked:
@@ -396,9 +401,10 @@ class _SlabMeshPotential(torch.autograd.Function):
             slab = (lay.x0, lay.ns[0])
             if need_pos:
                 ops.gather_vjp(psi, pos, q, cfg.r2u, cfg.nodes, cfg.method, grad_positions=g_pos,
-                               values_out=g_q if need_q else None, epilogue=epi, slab=slab)
+                               values_out=g_q if need_q else None, epilogue=epi, slab=slab, point_list=plist)
             else:
-                ops.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi, slab=slab)
+                ops.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi, slab=slab,
+                           point_list=plist)
         if forked:
             torch.cuda.current_stream().wait_stream(_side_stream(q.device))
         flat = cfg.reducer.all_reduce(flat)
