@@ -236,8 +236,8 @@ __device__ __forceinline__ int skew(int p) { return p + (p >> 4); }
 
 template <typename T> struct MaxThreads { static constexpr int value = sizeof(T) == 8 ? 128 : 256; };
 
-template <typename T, typename GT, int N, int MODE, int GV>
-__global__ void __launch_bounds__(MaxThreads<T>::value, (sizeof(T) == 4 && MODE == 2 && GV == GV_ORTHO) ? 3 : 1)
+template <typename T, typename GT, int N, int MODE, int GV, bool REMOTE>
+__global__ void __launch_bounds__(MaxThreads<T>::value)
 lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, int64_t ls, int d1,
                  int64_t s1, int64_t s0, GreenDev<GT> green, int nx, int ny, int nz, T* __restrict__ dc_out,
                  int y_off, RemoteStore rs) {
@@ -256,10 +256,10 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
   const int o_hi = o / d1, o_lo = o - o_hi * d1;
   C2<T>* base = data + o_hi * s1 + o_lo * s0 + z0;
   // final stores: in place, or into the peers' buffers
-  const int64_t r_base = rs.enabled ? (int64_t)(o / rs.dA) * rs.sA + (int64_t)(o % rs.dA) * rs.sB + rs.off + z0 : 0;
+  const int64_t r_base = REMOTE ? (int64_t)(o / rs.dA) * rs.sA + (int64_t)(o % rs.dA) * rs.sB + rs.off + z0 : 0;
   const int r_mask = (1 << rs.shift) - 1;
   auto store_line = [&](int line, int c, C2<T> v) {
-    if (rs.enabled)
+    if (REMOTE)
       (reinterpret_cast<C2<T>*>(rs.p[line >> rs.shift]) + r_base)[(int64_t)(line & r_mask) * rs.sL + c] = v;
     else
       base[(int64_t)line * ls + c] = v;
@@ -867,11 +867,16 @@ int launch_lines(void* data, int n_outer, int n_inner, int64_t ls, int d1, int64
   threads = threads < 64 ? 64 : (threads > max_threads ? max_threads : (threads + 31) / 32 * 32);
   size_t smem = (Chain<N>::NG > 1 ? ((size_t)N * zc) : 0) * sizeof(C2<T>) + (N / 2) * sizeof(C2<T>);
   if (MODE == 2) smem += ((size_t)N + zc) * sizeof(AxisEntry<GT>);
-  auto kernel = lines_fft_kernel<T, GT, N, MODE, GV>;
-  if (int rc = allow_smem(kernel, smem)) return rc;
   RemoteStore remote;
   if (rs != nullptr) remote = *rs;
   else memset(&remote, 0, sizeof(remote));
+  // the variant whose final stores go to peer GPUs exists for the forward and the fused x pass only
+  auto kernel = lines_fft_kernel<T, GT, N, MODE, GV, false>;
+  if (rs != nullptr) {
+    if (MODE == 1) { set_last_error("fft", "no remote-store variant of the inverse pass"); return 3; }
+    kernel = lines_fft_kernel<T, GT, N, MODE, GV, (MODE != 1)>;
+  }
+  if (int rc = allow_smem(kernel, smem)) return rc;
   kernel<<<(unsigned)(n_outer * n_chunks), threads, smem, s>>>(
       (C2<T>*)data, n_inner, zc, n_chunks, ls, d1, s1, s0, green, nx, ny, nz, (T*)dc_out, y_off, remote);
   TPME_CUDA_OK(cudaGetLastError());

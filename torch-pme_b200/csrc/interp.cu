@@ -139,7 +139,7 @@ spread_kernel(const T* __restrict__ positions, const T* __restrict__ weights, in
 
 // ---------------------------------------------------------------------------------------
 // slab decomposition: list of the points whose stencil reaches into the x slab [x0, x0 + nxl)
-// (warp-aggregated append; the order inside the list is irrelevant to the results)
+// (block-aggregated append; the order inside the list is irrelevant to the results)
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -155,13 +155,24 @@ select_slab_points_kernel(const T* __restrict__ positions, int64_t n_points, Mat
     const int first = wrap_base<T>(base + T(1 - (nodes + 1) / 2), dims.n[0], dims.inv_n[0]);
     keep = touches_slab(first, nodes, dims.n[0], x0, nxl);
   }
+  // one global atomic per thread block: warp counts -> block offsets -> list slots
+  __shared__ int warp_count[8];
+  __shared__ int block_base;
   const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-  if (ballot == 0) return;
-  const int lane = threadIdx.x & 31;
-  int base_slot = 0;
-  if (lane == 0) base_slot = atomicAdd(count, __popc(ballot));
-  base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
-  if (keep) list[base_slot + __popc(ballot & ((1u << lane) - 1))] = (int)i;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_count[warp] = __popc(ballot);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+      const int c = warp_count[k];
+      warp_count[k] = total;
+      total += c;
+    }
+    block_base = total > 0 ? atomicAdd(count, total) : 0;
+  }
+  __syncthreads();
+  if (keep) list[block_base + warp_count[warp] + __popc(ballot & ((1u << lane) - 1))] = (int)i;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -435,8 +446,27 @@ gather_point_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
   }
 
   T gu[3] = {T(0), T(0), T(0)};  // vjp accumulator in mesh coordinates
+  T extra[3] = {T(0), T(0), T(0)};  // sum_c coef2 * dvalues2 of the fused backward epilogue
+  const bool with_extra = (MODE & 4) && epi.enabled && epi.coef2 != nullptr;
   for (int ch = 0; ch < n_channels; ++ch) {
     const T* src = mesh + ch * mesh_size;
+    // per-point operands of the epilogues: issued before the mesh loads so that their latency
+    // hides under the stencil loop
+    T cf = T(0), prev = T(0), addc = T(0);
+    if (valid) {
+      if (MODE & 4) cf = coef[point * n_channels + ch];
+      if ((MODE & 1) && epi.enabled) {
+        prev = values[point * n_channels + ch];
+        addc = epi.add_coef[point * n_channels + ch];
+      }
+      if (with_extra) {
+        const T c2 = epi.coef2[point * n_channels + ch];
+        const T* d2 = epi.dvalues2 + (point * n_channels + ch) * 3;
+        extra[0] = fma_t(c2, d2[0], extra[0]);
+        extra[1] = fma_t(c2, d2[1], extra[1]);
+        extra[2] = fma_t(c2, d2[2], extra[2]);
+      }
+    }
     T val = T(0), du0 = T(0), du1 = T(0), du2 = T(0);
     if (any_inside) {
 #pragma unroll(N <= 5 ? N : 1)
@@ -474,8 +504,7 @@ gather_point_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
       if (MODE & 1) {
         const int64_t oidx = point * n_channels + ch;
         if (epi.enabled)
-          values[oidx] = values[oidx] + epi.scale * val - epi.add_coef[oidx] * epi.self_half -
-                         epi.background * epi.dc[ch];
+          values[oidx] = prev + epi.scale * val - addc * epi.self_half - epi.background * epi.dc[ch];
         else
           values[oidx] = val;
       }
@@ -486,7 +515,6 @@ gather_point_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
           out[b] = r2u.m[3 * b] * du0 + r2u.m[3 * b + 1] * du1 + r2u.m[3 * b + 2] * du2;
       }
       if (MODE & 4) {
-        const T cf = coef[point * n_channels + ch];
         gu[0] = fma_t(cf, du0, gu[0]);
         gu[1] = fma_t(cf, du1, gu[1]);
         gu[2] = fma_t(cf, du2, gu[2]);
@@ -499,11 +527,7 @@ gather_point_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
 #pragma unroll
       for (int b = 0; b < 3; ++b) {
         T g = r2u.m[3 * b] * gu[0] + r2u.m[3 * b + 1] * gu[1] + r2u.m[3 * b + 2] * gu[2];
-        if (epi.enabled && epi.coef2 != nullptr) {
-          for (int ch = 0; ch < n_channels; ++ch)
-            g = fma_t(epi.coef2[point * n_channels + ch], epi.dvalues2[(point * n_channels + ch) * 3 + b], g);
-          g *= epi.vjp_scale;
-        }
+        if (with_extra) g = (g + extra[b]) * epi.vjp_scale;
         out[b] = accumulate ? out[b] + g : g;
       }
     }
