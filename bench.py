@@ -309,15 +309,17 @@ def run_b200(args, wl):
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = h_forces.numel() * h_forces.element_size() + h_energy.element_size()
 
-    def e2e_step():
-        # public API, pinned host inputs -> static device buffers -> replay -> pinned host outputs
-        energy, g_pos, _ = graphed(positions=host["positions"], charges=host["charges"],
-                                   neighbor_indices=host["neighbor_indices"],
-                                   neighbor_distances=host["neighbor_distances"])
-        h_forces.copy_(g_pos, non_blocking=True)
-        h_energy.copy_(energy, non_blocking=True)
+    # the graph itself reads the pinned host inputs and writes the pinned host outputs
+    # (GraphedStep(host_io=True)): one replay is a complete host-to-host step
+    graphed_io = None
+    if graphed is not None:
+        graphed_io = tp.GraphedStep(calc, q, cell, inputs["positions"], idx, inputs["neighbor_distances"],
+                                    warmup=1, host_io=True)
 
-    if graphed is None:
+    def e2e_step():
+        graphed_io.replay()
+
+    if graphed_io is None:
         e2e_step = None
 
     def e2e_eager_step():
@@ -425,8 +427,9 @@ def run_b200(args, wl):
             "e2e": {"value": (1 if slab else world) * n_atoms * args.steps / (e2e_ms * 1e-3), "unit": "atom-steps/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d - host["cell"].numel() * host["cell"].element_size(),
                     "d2h_bytes_per_step": d2h,
-                    "path": "torchpme_b200.GraphedStep: pinned host positions/charges/neighbor list copied into the "
-                            "captured step's static buffers, graph replay, forces + energy copied back to pinned host",
+                    "path": "torchpme_b200.GraphedStep(host_io=True): one graph replay = H2D of positions/charges/"
+                            "neighbor list from pinned host memory (the pair list on the real-space branch, "
+                            "overlapping the mesh pipeline), the step, D2H of forces + energy into pinned host memory",
                     "eager_ms_per_step": e2e_eager_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
@@ -437,6 +440,8 @@ def run_b200(args, wl):
         torch.cuda.synchronize()
         if graphed is not None:
             graphed.release()
+        if graphed_io is not None:
+            graphed_io.release()
         dist.barrier()
         torch.cuda.synchronize()
         dist.destroy_process_group()

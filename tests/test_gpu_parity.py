@@ -219,3 +219,16 @@ def test_graphed_step_matches_eager():
         assert rel_err(e, e2.detach()) < 1e-5
         assert rel_err(gp, gp2) < 1e-4
         assert rel_err(gd, gd2) < 1e-5
+    # host_io: the graph reads pinned host inputs and writes pinned host outputs
+    graphed_io = tp.GraphedStep(calc, q, cell, pos, idx, d, host_io=True)
+    for shift in (0.0, 0.05):
+        new_pos = pos + shift
+        graphed_io.host["positions"].copy_(new_pos.cpu())
+        graphed_io.replay()
+        torch.cuda.synchronize()
+        p2 = new_pos.clone().requires_grad_(True)
+        V2 = calc(q, cell, p2, idx, d)
+        e2 = (V2 * q).sum()
+        (gp2,) = torch.autograd.grad(e2, (p2,))
+        assert rel_err(graphed_io.host["energy"], e2.detach()) < 1e-5
+        assert rel_err(graphed_io.host["grad_positions"], gp2) < 1e-4

@@ -10,6 +10,12 @@ each, while Python needs ~0.5 ms to issue them.  :class:`GraphedStep` captures
 once into a ``torch.cuda.CUDAGraph`` over static buffers and replays it; new inputs (host or
 device tensors of the captured shapes) are copied into the static buffers first.  The cell
 geometry, mesh size and neighbor-list length are frozen at capture time.
+
+With ``host_io=True`` the host <-> device traffic is part of the graph: the step's inputs are read
+from pinned host staging tensors (``.host["positions"]`` ...), the energy and forces land in pinned
+host tensors (``.host["energy"]``, ``.host["grad_positions"]``).  The neighbor-list copy runs on the
+graph branch of the real-space kernels, so the mesh pipeline (which only needs positions and
+charges) overlaps it; one ``replay()`` + ``synchronize()`` is a complete host-to-host step.
 """
 
 from __future__ import annotations
@@ -21,7 +27,7 @@ from .mesh import set_nan_check
 
 class GraphedStep:
     def __init__(self, calculator, charges, cell, positions, neighbor_indices, neighbor_distances,
-                 warmup: int = 3):
+                 warmup: int = 3, host_io: bool = False):
         dev = positions.device
         if dev.type != "cuda":
             raise ValueError("GraphedStep needs CUDA tensors")
@@ -37,11 +43,26 @@ class GraphedStep:
             self.positions = positions.detach().clone().requires_grad_(True)
             self.neighbor_indices = neighbor_indices.detach().clone()
             self.neighbor_distances = neighbor_distances.detach().clone().requires_grad_(True)
+            self.host = None
+            if host_io:
+                self.host = {
+                    "positions": positions.detach().cpu().pin_memory(),
+                    "charges": charges.detach().cpu().pin_memory(),
+                    "neighbor_indices": neighbor_indices.detach().cpu().pin_memory(),
+                    "neighbor_distances": neighbor_distances.detach().cpu().pin_memory(),
+                    "energy": torch.empty((), dtype=positions.dtype).pin_memory(),
+                    "grad_positions": torch.empty(positions.shape, dtype=positions.dtype).pin_memory(),
+                }
             for _ in range(max(1, warmup)):
                 self._step()
             self.stream.synchronize()
             with torch.cuda.graph(self.graph, stream=self.stream):
+                if host_io:
+                    self._copy_in()
                 self.energy, self.grad_positions, self.grad_distances = self._step()
+                if host_io:
+                    self.host["grad_positions"].copy_(self.grad_positions, non_blocking=True)
+                    self.host["energy"].copy_(self.energy, non_blocking=True)
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
         # exchange buffers of a slab-decomposed calculator are baked into the graph: keep them alive
@@ -51,6 +72,22 @@ class GraphedStep:
         """drop the captured graph (call before destroying a process group whose collectives it holds)"""
         self.graph.reset()
         self._keepalive = None
+
+    @torch.no_grad()
+    def _copy_in(self):
+        """captured host -> device copies; the pair list goes over the real-space branch"""
+        from .calculators import _side_stream
+
+        main = torch.cuda.current_stream()
+        side = _side_stream(self.positions.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.neighbor_distances.copy_(self.host["neighbor_distances"], non_blocking=True)
+            self.neighbor_indices.copy_(self.host["neighbor_indices"], non_blocking=True)
+        self.positions.copy_(self.host["positions"], non_blocking=True)
+        self.charges.copy_(self.host["charges"], non_blocking=True)
+        # the calculator forks the real-space kernels onto `side` (ordered after the copies above)
+        # and joins before it needs them; every other consumer of the pair list sits behind that join
 
     def _step(self):
         V = self.calculator(self.charges, self.cell, self.positions, self.neighbor_indices,
