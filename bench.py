@@ -319,8 +319,16 @@ def run_b200(args, wl):
     def e2e_step():
         graphed_io.replay()
 
+    def e2e_copy_step():
+        # same public API without host_io: async copies into the static buffers, replay, copies back
+        energy, g_pos, _ = graphed(positions=host["positions"], charges=host["charges"],
+                                   neighbor_indices=host["neighbor_indices"],
+                                   neighbor_distances=host["neighbor_distances"])
+        h_forces.copy_(g_pos, non_blocking=True)
+        h_energy.copy_(energy, non_blocking=True)
+
     if graphed_io is None:
-        e2e_step = None
+        e2e_step = e2e_copy_step = None
 
     def e2e_eager_step():
         c_pos = host["positions"].to(device, non_blocking=True).requires_grad_(True)
@@ -335,7 +343,12 @@ def run_b200(args, wl):
         h_energy.copy_(energy.detach(), non_blocking=True)
 
     e2e_eager_ms = timed(e2e_eager_step, args.steps, warm)
-    e2e_ms = timed(e2e_step, args.steps, warm) if e2e_step is not None else e2e_eager_ms
+    e2e_variants = {"eager launches": e2e_eager_ms}
+    if e2e_step is not None:
+        e2e_variants["GraphedStep(host_io=True)"] = timed(e2e_step, args.steps, warm)
+        e2e_variants["GraphedStep + explicit copies"] = timed(e2e_copy_step, args.steps, warm)
+    e2e_best = min(e2e_variants, key=e2e_variants.get)
+    e2e_ms = e2e_variants[e2e_best]
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-stage roofline (rank 0): each stage timed alone, L2 flushed before every launch ----
@@ -427,9 +440,10 @@ def run_b200(args, wl):
             "e2e": {"value": (1 if slab else world) * n_atoms * args.steps / (e2e_ms * 1e-3), "unit": "atom-steps/s",
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d - host["cell"].numel() * host["cell"].element_size(),
                     "d2h_bytes_per_step": d2h,
-                    "path": "torchpme_b200.GraphedStep(host_io=True): one graph replay = H2D of positions/charges/"
-                            "neighbor list from pinned host memory (the pair list on the real-space branch, "
-                            "overlapping the mesh pipeline), the step, D2H of forces + energy into pinned host memory",
+                    "path": f"torchpme_b200 public API, fastest of the variants below ({e2e_best}): H2D of positions/"
+                            "charges/neighbor list from pinned host memory, the step, D2H of forces + energy into "
+                            "pinned host memory, all inside the timed region",
+                    "variants_ms_per_step": {k: round(v / args.steps, 5) for k, v in e2e_variants.items()},
                     "eager_ms_per_step": e2e_eager_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
