@@ -21,13 +21,13 @@ PY
 done
 python bench.py --impl reference --steps 3 > $out/${tag}_bench_reference_c2.json 2>/dev/null; cat $out/${tag}_bench_reference_c2.json | cut -c1-200
 # launch list (cold-cache, serialised: shares only)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_c2.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
+    --log-file $out/${tag}_launches_c2.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --profiler-range > /dev/null 2>&1
 # full captures of the hot kernels (eager warm-up launches of the step)
 for w in c2 c4; do
   ncu --set full --clock-control none --import-source on \
       -k 'regex:gather_point|spread_kernel|lines_fft|plane_r2c|plane_c2r|rows_r2c|rows_c2r|pair_forward|pair_backward' -c 12 \
-      -o $out/${tag}_full_$w -f python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+      --profile-from-start off -o $out/${tag}_full_$w -f python bench.py --workload $w --steps 2 --warmup 1 --no-cpu-baseline --profiler-range > /dev/null 2>&1
   # the report files are too large to travel back: export the raw metrics page and drop them
   ncu -i $out/${tag}_full_$w.ncu-rep --page raw --csv > $out/${tag}_ncu_full_$w.csv 2>/dev/null
   rm -f $out/${tag}_full_$w.ncu-rep

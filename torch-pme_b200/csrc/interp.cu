@@ -248,7 +248,9 @@ gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
 #pragma unroll
     for (int a = 0; a < N; ++a) {
       const unsigned lx = (unsigned)(ix - x0);
-      xoff[a] = lx < (unsigned)nxl ? lx * plane : kOutside;
+      const bool inside = lx < (unsigned)nxl;   // planes outside the slab: zero weight, loads redirected
+      xoff[a] = inside ? lx * plane : 0u;
+      if (!inside) { w[0][a] = T(0); if (DERIV) dw[0][a] = T(0); }
       yoff[a] = (unsigned)iy * nz;
       ix = (ix + 1 >= nx) ? wrap_add(ix + 1, nx) : ix + 1;
       iy = (iy + 1 >= ny) ? wrap_add(iy + 1, ny) : iy + 1;
@@ -265,7 +267,6 @@ gather_kernel(const T* __restrict__ mesh, const T* __restrict__ positions,
     T s0 = T(0), s1 = T(0), s2 = T(0);
 #pragma unroll
     for (int a = 0; a < N; ++a) {
-      if (xoff[a] == kOutside) continue;
       T t0 = T(0), t1 = T(0);
 #pragma unroll
       for (int b = 0; b < N; ++b) {
