@@ -52,8 +52,10 @@ def test_full_size_properties(name):
     assert n == wl["n_side"] ** 3
 
     V64, gp64, gd64 = _step(calc, q64, cell64, pos64, idx, d64)
-    # ---- momentum conservation of the energy step (fp64): |sum F| << sum |F|
-    assert float(gp64.sum(0).abs().max()) < 1e-6 * float(gp64.abs().sum())
+    # ---- net force of the energy step (fp64): mesh Ewald with differentiated weights conserves
+    # energy, not momentum -- the residual is the (small) mesh self-force, a sanity bound only
+    net = float(gp64.sum(0).abs().max()) / float(gp64.abs().sum())
+    assert net < 1e-2
 
     # ---- fp32 kernels against fp64 kernels, north-star tolerance 1e-3
     pos, q, cell, d = pos64.float(), q64.float(), cell64.float(), d64.float()
@@ -90,3 +92,6 @@ def test_full_size_properties(name):
     assert rel_err(graphed.grad_distances, ref[2]) < (1e-10 if dt == torch.float64 else 1e-4)
     # spread atomics reorder between runs: compare forces loosely in fp32
     assert rel_err(graphed.grad_positions, ref[1]) < (1e-9 if dt == torch.float64 else 1e-3)
+    print(f"\n[{name}] N={n}: net force/sum|F| {net:.2e}; fp32 vs fp64: V {rel_err(V32, V64):.2e}, dE/dd "
+          f"{rel_err(gd32, gd64):.2e}, forces max {err.max() / fmax:.2e}, L2 {np.linalg.norm(err) / float(gp64.norm()):.2e}; "
+          f"linearity {rel_err(Va + 2 * Vb, Vab):.2e}")
