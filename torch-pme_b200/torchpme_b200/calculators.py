@@ -82,13 +82,15 @@ class _FusedMeshPotential(torch.autograd.Function):
         d = distances.detach().contiguous()
         idx = neighbor_indices.contiguous()
         need_pos = ctx.needs_input_grad[1]
-        out = torch.zeros_like(q)
-        # the pair sum is independent of the mesh pipeline until the gather epilogue: run it on a
-        # side stream (a parallel branch when the step is captured in a CUDA graph)
+        out = torch.empty_like(q)
+        # the pair sum is independent of the mesh pipeline until the gather epilogue: run it (and
+        # the zero fill of its accumulator) on a side stream -- a parallel branch when the step is
+        # captured in a CUDA graph.  `out` is next touched on the main stream after the join.
         main = torch.cuda.current_stream()
         side = _side_stream(q.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            out.zero_()
             _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
         rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
         green = _native.make_green(scale=1.0, **cfg.green_args)

@@ -33,6 +33,7 @@ class GraphedStep:
             raise ValueError("GraphedStep needs CUDA tensors")
         self.calculator = calculator
         self.stream = torch.cuda.Stream(device=dev)
+        self.aux = torch.cuda.Stream(device=dev)     # side branch of the energy reduction
         self.graph = torch.cuda.CUDAGraph()
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         set_nan_check(False)  # the eager NaN guard is a host sync and cannot be captured
@@ -92,9 +93,17 @@ class GraphedStep:
     def _step(self):
         V = self.calculator(self.charges, self.cell, self.positions, self.neighbor_indices,
                             self.neighbor_distances)
-        energy = (V * self.charges).sum()
-        g_pos, g_d = torch.autograd.grad(energy, (self.positions, self.neighbor_distances))
-        return energy.detach(), g_pos, g_d
+        # E = sum_i q_i V_i: its reduction is a side branch of the graph, and the backward is seeded
+        # directly with dE/dV = q (a vector-Jacobian product) instead of going through the tape of
+        # the multiply + sum -- same numbers, three small kernels fewer on the critical path
+        main = torch.cuda.current_stream()
+        self.aux.wait_stream(main)
+        with torch.cuda.stream(self.aux):
+            energy = (V.detach() * self.charges).sum()
+        g_pos, g_d = torch.autograd.grad(V, (self.positions, self.neighbor_distances),
+                                         grad_outputs=self.charges)
+        main.wait_stream(self.aux)
+        return energy, g_pos, g_d
 
     def replay(self) -> None:
         self.graph.replay()
