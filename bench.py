@@ -262,21 +262,24 @@ def run_b200(args, wl):
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
-    def timed(run, steps, warmup):
+    def timed(run, steps, warmup, collective=True):
+        """device time of `steps` calls (CUDA events, L2 flushed before each); with `collective` the
+        ranks enter and leave together and the result is the max over ranks"""
+        collective = collective and world > 1
         for _ in range(warmup):
             flush.zero_(); run()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        if world > 1:
+        if collective:
             dist.barrier()
         torch.cuda.synchronize()
         for a, b in evs:
             flush.zero_()
             a.record(); run(); b.record()
         torch.cuda.synchronize()
-        if world > 1:
+        if collective:
             dist.barrier()
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        if world > 1:
+        if collective:
             t = torch.tensor([total_ms], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t)
@@ -393,7 +396,8 @@ def run_b200(args, wl):
         peak, peak_src = measured_peak()
         stages = {}
         for name, fn in stage_fns.items():
-            ms = timed(fn, max(10, args.steps), 3) / max(10, args.steps)
+            # rank 0 only: no collectives inside
+            ms = timed(fn, max(10, args.steps), 3, collective=False) / max(10, args.steps)
             stages[name] = {"ms": round(ms, 5), "alg_bytes": alg[name],
                             "gbs": round(alg[name] / ms / 1e6, 1), "frac": round(alg[name] / ms / 1e6 / peak, 4)}
         # time per step spent in each kind of stage (spread and kfilter run twice per step)
