@@ -7,6 +7,8 @@ torchpme_b200 -- B200-native PME / P3M long-range calculators behind the torch-p
 
 Only the hot path of the reference is provided: PME / P3M calculators,
 Coulomb and inverse-power-law potentials, the mesh interpolator and k-space filter blocks.
+``torchpme_b200.distributed`` holds the slab-decomposed (one system over several GPUs) variants,
+``torchpme_b200.GraphedStep`` the CUDA-graph capture of an energy + forces step.
 """
 
 from . import calculators, graphs, lib, mesh, potentials, prefactors  # noqa: F401
