@@ -329,7 +329,8 @@ class PotentialSpec:
         if kind not in ("coulomb", "ipl"):
             raise ValueError(kind)
         self.kind = kind
-        self.smearing = float(smearing)
+        # None: no range separation (direct calculator, calculators/calculator.py:53-61)
+        self.smearing = None if smearing is None else float(smearing)
         self.exponent = int(exponent) if kind == "ipl" else 1
         self.prefactor = float(prefactor)
         self.exclusion_radius = exclusion_radius
@@ -478,10 +479,21 @@ def kspace_filter(mesh: np.ndarray, kfilter: np.ndarray, fft_norm="ortho", ifft_
 # calculators
 # --------------------------------------------------------------------------------------
 def compute_rspace(pot: PotentialSpec, charges, neighbor_indices, neighbor_distances,
-                   full_neighbor_list=False, closed_form=False):
-    """V_i = 1/2 sum_(i,j) q_j v_SR(d_ij)   (calculators/calculator.py:43-87)."""
+                   full_neighbor_list=False, closed_form=False, pair_mask=None):
+    """
+    V_i = 1/2 sum_(i,j) q_j v(d_ij)   (calculators/calculator.py:43-87): v = v_SR with a smearing,
+    the bare potential (times 1 - f_cut if an exclusion radius is set) without one (:53-61);
+    masked pairs contribute nothing (potential.py:106-138, `* pair_mask`).
+    """
     d = neighbor_distances
-    v = pot.sr_from_dist_closed(d) if closed_form else pot.sr_from_dist(d)
+    if pot.smearing is None:
+        v = pot.from_dist(d)
+        if pot.exclusion_radius is not None:
+            v = v * (1 - pot.f_cutoff(d))
+    else:
+        v = pot.sr_from_dist_closed(d) if closed_form else pot.sr_from_dist(d)
+    if pair_mask is not None:
+        v = v * pair_mask
     ii = neighbor_indices[:, 0]
     jj = neighbor_indices[:, 1]
     out = np.zeros_like(charges)
