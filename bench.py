@@ -339,6 +339,21 @@ def run_b200(args, wl):
     graph_ms = timed(graphed.replay, args.steps, warm) if graphed is not None else eager_ms
     if args.profiler_range:
         torch.cuda.profiler.stop()
+    fused = None
+    if args.fused and not slab:
+        # EXPERIMENTAL, opt-in: the step through calculator.energy_and_gradients() (one filter pass;
+        # SURVEY.md section 8d "fused energy+forces path"), reported next to the autograd step
+        try:
+            g_fused = tp.GraphedStep(calc, q, cell, inputs["positions"], idx, inputs["neighbor_distances"],
+                                     warmup=1, fused_energy_gradients=True)
+            fused_ms = timed(g_fused.replay, args.steps, warm)
+            fused = {"ms_per_step": fused_ms / args.steps,
+                     "value": world * n_atoms * args.steps / (fused_ms * 1e-3), "unit": "atom-steps/s",
+                     "note": "energy, dE/dpositions, dE/ddistances from one spread / filter / gather "
+                             "(calculator.energy_and_gradients); not the headline"}
+            g_fused.release()
+        except Exception as exc:
+            fused = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # ---- end to end through the public API: pinned host inputs -> device, forces -> host ----
     host = {k: inputs[k].detach().cpu().pin_memory() for k in
@@ -493,6 +508,7 @@ def run_b200(args, wl):
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "stages": stages, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "fused_energy_gradients": fused,
         }
         print(json.dumps(line), flush=True)
     if world > 1 or slab:
@@ -517,6 +533,8 @@ def main():
     ap.add_argument("--decomposition", default="replica", choices=["replica", "slab"])
     ap.add_argument("--transport", default="nccl", choices=["nccl", "p2p", "p2p-copy"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
+    ap.add_argument("--fused", action="store_true",
+                    help="also time the experimental one-filter-pass energy + gradients step")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the steps (for ncu --profile-from-start off)")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 5 eager steps to this file")

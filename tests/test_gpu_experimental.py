@@ -1,0 +1,39 @@
+"""
+Opt-in GPU tests of EXPERIMENTAL entry points that have not been measured / validated on a GPU
+yet (run with TPME_EXPERIMENTAL=1); they are skipped by default so that an unvalidated path can
+never mask the status of the validated ones.
+"""
+import os
+
+import pytest
+import torch
+
+from helpers import rel_err, rocksalt
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("TPME_EXPERIMENTAL") != "1", reason="set TPME_EXPERIMENTAL=1")]
+
+
+@pytest.mark.parametrize("method, dtype", [("P3M", torch.float64), ("PME", torch.float64), ("P3M", torch.float32)])
+def test_energy_and_gradients_matches_autograd(method, dtype):
+    import torchpme_b200 as tp
+
+    pos, q, cell, idx, d = rocksalt(8, dtype=dtype, device="cuda")
+    q = torch.cat([q, 0.4 * q + 0.2], dim=1)
+    cls = tp.P3MCalculator if method == "P3M" else tp.PMECalculator
+    calc = cls(tp.CoulombPotential(smearing=1.2).to("cuda"), mesh_spacing=float(cell[0, 0]) / 14)
+    p = pos.clone().requires_grad_(True)
+    dd = d.clone().requires_grad_(True)
+    V = calc(q, cell, p, idx, dd)
+    energy = (V * q).sum()
+    gp, gd = torch.autograd.grad(energy, (p, dd))
+    e2, gp2, gd2, V2 = calc.energy_and_gradients(q, cell, pos, idx, d)
+    tol = 1e-10 if dtype == torch.float64 else 1e-4
+    assert rel_err(V2, V.detach()) < tol
+    assert abs(float(e2) - float(energy)) < tol * abs(float(energy))
+    assert rel_err(gd2, gd) < tol
+    assert rel_err(gp2, gp) < tol * 10
+    graphed = tp.GraphedStep(calc, q, cell, pos, idx, d, fused_energy_gradients=True)
+    graphed.replay()
+    torch.cuda.synchronize()
+    assert rel_err(graphed.grad_positions, gp) < tol * 10 and rel_err(graphed.grad_distances, gd) < tol

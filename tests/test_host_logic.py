@@ -152,3 +152,25 @@ def test_kvectors_match_oracle():
     for ns in ((4, 5, 6), (7, 3, 8), (1, 1, 1)):
         kv = tp.lib.generate_kvectors_for_mesh(torch.tensor(cell), torch.tensor(ns))
         np.testing.assert_allclose(kv.numpy(), oracle.kvectors_for_mesh(cell, ns), rtol=1e-13, atol=1e-14)
+
+
+def test_fused_config_is_host_only_and_cached():
+    """the by-value launch parameters of the fast path are pure host arithmetic"""
+    calc = tp.P3MCalculator(tp.CoulombPotential(smearing=1.2, prefactor=2.0), mesh_spacing=1.5,
+                            interpolation_nodes=4)
+    cell = torch.eye(3, dtype=torch.float64) * 12.0
+    cfg = calc._fused_config(cell)
+    assert cfg.ns == (32, 32, 32) and cfg.nodes == 4 and cfg.method == 0 and cfg.full_list is False
+    assert abs(cfg.half_ivolume - 0.5 / 12.0**3) < 1e-18
+    assert abs(cfg.self_half - 0.5 * 2.0 * np.sqrt(2 / np.pi) / 1.2) < 1e-14
+    assert abs(cfg.background_ivolume - 2.0 * np.pi * 1.2**2 / 12.0**3) < 1e-16
+    assert cfg.green_args["p3m_nodes"] == 4 and cfg.green_args["kind"] == 1
+    np.testing.assert_allclose(np.asarray(cfg.r2u).reshape(3, 3), np.eye(3) * 32 / 12.0, rtol=1e-15)
+    assert calc._fused_config(cell) is cfg                      # same cell tensor: cached
+    pme = tp.PMECalculator(tp.InversePowerLawPotential(exponent=6, smearing=1.0), mesh_spacing=1.5)
+    cfg2 = pme._fused_config(cell)
+    assert cfg2.method == 1 and cfg2.green_args["p3m_nodes"] == 0 and cfg2.green_args["exponent"] == 6
+    assert cfg2.background_ivolume == 0.0
+    with pytest.raises(tp.NativeLibraryError, match="CUDA-only"):
+        calc.energy_and_gradients(torch.ones(2, 1, dtype=torch.float64), cell, torch.zeros(2, 3, dtype=torch.float64),
+                                  torch.zeros(1, 2, dtype=torch.int64), torch.ones(1, dtype=torch.float64))

@@ -242,6 +242,13 @@ class PMECalculator(Calculator):
                 f"`positions` lives on {positions.device}; torchpme_b200 is a CUDA-only implementation "
                 "(no CPU fallback). Move the inputs to a CUDA device."
             )
+        cfg = self._fused_config(cell)
+        mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
+        return _FusedMeshPotential.apply(charges, positions, neighbor_distances, neighbor_indices,
+                                         mask_u8, cfg)
+
+    def _fused_config(self, cell) -> _FusedStepConfig:
+        """by-value launch parameters of the fast path, cached per (cell geometry, potential scalars)"""
         pot = self.potential
         geom = geometry_of(cell)
         ns = geom.ns_mesh(self.mesh_spacing)
@@ -265,9 +272,56 @@ class PMECalculator(Calculator):
             cfg.self_half = 0.5 * float(pot.self_contribution())
             cfg.background_ivolume = float(pot.background_correction()) * ivolume
             self._fused_cfg, self._fused_key, self._fused_geom = cfg, key, geom
+        return cfg
+
+    @torch.no_grad()
+    def energy_and_gradients(self, charges, cell, positions, neighbor_indices, neighbor_distances,
+                             pair_mask=None):
+        """
+        EXPERIMENTAL (not part of the reference API, not yet measured on a GPU):
+        ``E = sum_ic q_ic V_ic`` with ``dE/dpositions`` and ``dE/dneighbor_distances`` from ONE
+        spread, ONE filter pass and ONE gather.  The autograd backward of ``E`` spreads the incoming
+        gradient ``dE/dV = q`` and filters it again; because the filter is self-adjoint that mesh
+        equals the forward one, so the two derivative gathers coincide:
+
+            dE/dr_i = (1 / Vol) sum_c q_ic  d/dr_i [gather(phi_c)]_i ,   phi = A spread(q)
+
+        ("fused energy+forces path").  Same restrictions as the fast path of
+        :meth:`forward`; returns ``(E, dE/dpositions, dE/dneighbor_distances, V)``.
+        """
+        if not self._fast_path_ok(cell, None, None, None):
+            raise NotImplementedError(
+                "energy_and_gradients needs an in-kernel potential and no cell / parameter gradients")
+        validate_parameters(charges, cell, positions, neighbor_indices, neighbor_distances,
+                            None, pair_mask, None, None)
+        if not positions.is_cuda:
+            raise _native.NativeLibraryError(
+                f"`positions` lives on {positions.device}; torchpme_b200 is a CUDA-only implementation "
+                "(no CPU fallback). Move the inputs to a CUDA device.")
+        cfg = self._fused_config(cell)
+        q, pos = charges.detach().contiguous(), positions.detach().contiguous()
+        d, idx = neighbor_distances.detach().contiguous(), neighbor_indices.contiguous()
         mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
-        return _FusedMeshPotential.apply(charges, positions, neighbor_distances, neighbor_indices,
-                                         mask_u8, cfg)
+        out = torch.empty_like(q)
+        g_d = torch.empty(idx.shape[0], dtype=q.dtype, device=q.device)
+        main = torch.cuda.current_stream()
+        side = _side_stream(q.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            out.zero_()
+            _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
+            _native.pair_backward(q, idx, d, None, mask_u8, q, cfg.full_list, cfg.pair_pot,
+                                  want_charges=False, want_pairs=True, grad_pairs_out=g_d)
+        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+        green = _native.make_green(scale=1.0, **cfg.green_args)
+        phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
+        main.wait_stream(side)
+        epi = _native.make_epilogue(q, dc, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume)
+        _, dvalues = _native.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=True,
+                                    values_out=out, epilogue=epi)
+        g_pos = torch.einsum("ic,icd->id", q, dvalues) * (2.0 * cfg.half_ivolume)
+        energy = (out * q).sum()
+        return energy, g_pos, g_d, out
 
     def _compute_kspace(self, charges, cell, positions, periodic=None, node_mask=None, kvectors=None):
         if node_mask is not None or kvectors is not None:

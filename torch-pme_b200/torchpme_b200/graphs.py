@@ -27,8 +27,10 @@ from .mesh import set_nan_check
 
 class GraphedStep:
     def __init__(self, calculator, charges, cell, positions, neighbor_indices, neighbor_distances,
-                 warmup: int = 3, host_io: bool = False):
+                 warmup: int = 3, host_io: bool = False, fused_energy_gradients: bool = False):
         dev = positions.device
+        # EXPERIMENTAL: one filter pass per step through calculator.energy_and_gradients()
+        self.fused_energy_gradients = fused_energy_gradients
         if dev.type != "cuda":
             raise ValueError("GraphedStep needs CUDA tensors")
         self.calculator = calculator
@@ -91,6 +93,10 @@ class GraphedStep:
         # and joins before it needs them; every other consumer of the pair list sits behind that join
 
     def _step(self):
+        if self.fused_energy_gradients:
+            energy, g_pos, g_d, _ = self.calculator.energy_and_gradients(
+                self.charges, self.cell, self.positions, self.neighbor_indices, self.neighbor_distances)
+            return energy, g_pos, g_d
         V = self.calculator(self.charges, self.cell, self.positions, self.neighbor_indices,
                             self.neighbor_distances)
         # E = sum_i q_i V_i: its reduction is a side branch of the graph, and the backward is seeded
