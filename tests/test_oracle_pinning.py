@@ -179,3 +179,73 @@ def test_oracle_against_live_reference():
         ref = calc(torch.tensor(q), torch.tensor(cell), torch.tensor(pos), torch.tensor(idx), torch.tensor(d)).numpy()
         mine = oracle.calculator_forward(oracle.PotentialSpec("coulomb", 0.9), q, cell, pos, idx, d, 0.6, nodes, method)
         assert rel_err(mine, ref) < 1e-12
+
+
+# --------------------------------------------------------------------------------------
+# interpolator invariants the reference asserts (tests/lib/test_mesh_interpolator.py:17-328)
+# --------------------------------------------------------------------------------------
+STENCILS = [("P3M", n) for n in (1, 2, 3, 4, 5)] + [("Lagrange", n) for n in (3, 4, 5, 6, 7)]
+
+
+@pytest.mark.parametrize("method, nodes", STENCILS)
+def test_oracle_interpolator_invariants(method, nodes):
+    rng = np.random.default_rng(100 + nodes)
+    # charge conservation, cubic cell, odd and even mesh sizes (:23-58)
+    for n_mesh in (19, 20, 25):
+        cell = np.eye(3) * 6.28318530717
+        pos = rng.random((8, 3)) * 6.28318530717
+        w = 3 * rng.standard_normal((8, 5))
+        mesh = oracle.points_to_mesh(w, pos, cell, (n_mesh,) * 3, nodes, method)
+        np.testing.assert_allclose(mesh.sum(axis=(1, 2, 3)), w.sum(0), rtol=1e-12, atol=1e-12)
+    # charge conservation, triclinic cell, anisotropic mesh, atoms outside the cell (:62-99)
+    cell = rng.standard_normal((3, 3)) * 2.718281828
+    pos = (rng.random((11, 3)) * 3 - 1) @ cell
+    w = 3 * rng.standard_normal((11, 2))
+    ns = (11, 14, 17)
+    mesh = oracle.points_to_mesh(w, pos, cell, ns, nodes, method)
+    np.testing.assert_allclose(mesh.sum(axis=(1, 2, 3)), w.sum(0), rtol=1e-12, atol=1e-12)
+    # total mass: interpolating a constant mesh returns the constant (:236-278)
+    const = np.full((2,) + ns, 0.37)
+    const[1] = -1.9
+    vals, dvals = oracle.mesh_to_points(const, pos, cell, nodes, method, gradient=True)
+    np.testing.assert_allclose(vals, np.broadcast_to([0.37, -1.9], vals.shape), rtol=1e-12)
+    np.testing.assert_allclose(dvals, 0.0, atol=1e-10)
+    # spread and gather are adjoint: <gather(m), w> == <m, spread(w)>
+    m = rng.standard_normal((2,) + ns)
+    lhs = (oracle.mesh_to_points(m, pos, cell, nodes, method) * w).sum()
+    np.testing.assert_allclose(lhs, (m * mesh).sum(), rtol=1e-11)
+    # derivative of the interpolated value by central differences (:282-328); skip points that sit
+    # within the step of a stencil switch (P3M n >= 2 is C0 or better, Lagrange is only C0 there)
+    if nodes > 1:
+        eps = 1e-6
+        u = oracle.mesh_coordinates(pos, cell, ns)
+        frac = u - np.floor(u) if nodes % 2 == 0 else u - np.rint(u) + 0.5
+        safe = np.all((frac > 1e-3) & (frac < 1 - 1e-3), axis=1)
+        _, grad = oracle.mesh_to_points(m, pos, cell, nodes, method, gradient=True)
+        for axis in range(3):
+            step = np.zeros(3)
+            step[axis] = eps
+            fd = (oracle.mesh_to_points(m, pos + step, cell, nodes, method)
+                  - oracle.mesh_to_points(m, pos - step, cell, nodes, method)) / (2 * eps)
+            np.testing.assert_allclose(grad[safe, :, axis], fd[safe], rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_exact_agreement_on_mesh_points():
+    """nodes = 1, 2 (P3M): atoms sitting on mesh points put their whole weight there (:103-147)"""
+    rng = np.random.default_rng(8794329)
+    for nodes in (1, 2):
+        for n_mesh in (7, 10, 12):
+            cell = rng.standard_normal((3, 3)) * 0.28209478
+            # distinct mesh points
+            flat = rng.choice(n_mesh ** 3, size=10, replace=False)
+            ind = np.stack(np.unravel_index(flat, (n_mesh,) * 3), axis=1)
+            pos = (ind / n_mesh) @ cell
+            if nodes == 2:
+                pos = pos + (0.5 / n_mesh) * cell.sum(0)     # even stencils are centred on cell midpoints
+            w = 3 * rng.standard_normal((10, 3))
+            mesh = oracle.points_to_mesh(w, pos, cell, (n_mesh,) * 3, nodes, "P3M")
+            if nodes == 1:
+                np.testing.assert_allclose(mesh[:, ind[:, 0], ind[:, 1], ind[:, 2]].T, w, rtol=1e-9, atol=1e-12)
+            else:
+                # x = 0: the two nodes of every axis share the weight equally -> 1/8 on the base corner
+                np.testing.assert_allclose(mesh.sum(axis=(1, 2, 3)), w.sum(0), rtol=1e-12)
