@@ -135,3 +135,50 @@ def test_slab_needs_process_group():
     calc = SlabP3MCalculator(tp.CoulombPotential(smearing=1.0), mesh_spacing=0.5)
     with pytest.raises(RuntimeError, match="torch.distributed has to be initialised"):
         calc(torch.ones(2, 1), torch.eye(3), torch.zeros(2, 3), torch.zeros(1, 2, dtype=torch.int64), torch.ones(1))
+
+
+@pytest.fixture()
+def gloo_world1():
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    yield
+    dist.destroy_process_group()
+
+
+def test_slab_restrictions_raise(gloo_world1):
+    """what the slab-decomposed path does not support fails loudly, before any kernel runs"""
+    import torchpme_b200 as tp
+    from slab_cpu_ops import CpuOps
+    from torchpme_b200.distributed import SlabP3MCalculator, SlabPMECalculator
+
+    dt = torch.float64
+    q, cell, pos = torch.ones(4, 1, dtype=dt), torch.eye(3, dtype=dt) * 8, torch.rand(4, 3, dtype=dt) * 8
+    idx, d = torch.tensor([[0, 1], [2, 3]]), torch.ones(2, dtype=dt)
+    calc = SlabP3MCalculator(tp.CoulombPotential(smearing=1.0), mesh_spacing=1.0, _ops=CpuOps())
+    with pytest.raises(NotImplementedError, match="3-D periodic systems only"):
+        calc(q, cell, pos, idx, d, periodic=torch.tensor([True, True, False]))
+    with pytest.raises(NotImplementedError, match="Batching not implemented"):
+        calc(q, cell, pos, idx, d, node_mask=torch.ones(4, dtype=torch.bool))
+    with pytest.raises(NotImplementedError, match="cell / potential-parameter gradients"):
+        calc(q, cell.clone().requires_grad_(True), pos, idx, d)
+
+    class Custom(tp.CoulombPotential):
+        pass
+
+    generic = SlabPMECalculator(Custom(smearing=1.0), mesh_spacing=1.0, _ops=CpuOps())
+    with pytest.raises(NotImplementedError, match="in-kernel potential"):
+        generic(q, cell, pos, idx, d)
+    with pytest.raises(ValueError, match="unknown transport"):
+        SlabP3MCalculator(tp.CoulombPotential(smearing=1.0), mesh_spacing=1.0, transport="mpi", _ops=CpuOps())(
+            q, cell, pos, idx, d)
+    # the product configuration (CUDA library, no injected ops) refuses CPU tensors
+    product = SlabP3MCalculator(tp.CoulombPotential(smearing=1.0), mesh_spacing=1.0)
+    with pytest.raises(tp.NativeLibraryError, match="CUDA-only"):
+        product(q, cell, pos, idx, d)
+    # world_size 1 through the emulation equals the single-process oracle
+    from oracle import pme_oracle as oracle
+    V = calc(q, cell, pos, idx, d)
+    ref = oracle.calculator_forward(oracle.PotentialSpec("coulomb", 1.0), q.numpy(), cell.numpy(), pos.numpy(),
+                                    idx.numpy(), d.numpy(), 1.0, 4, "P3M")
+    np.testing.assert_allclose(V.numpy(), ref, rtol=1e-10, atol=1e-12)
