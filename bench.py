@@ -40,6 +40,10 @@ WORKLOADS = {
 SMEARING = 1.2
 CUTOFF = 6.0
 NODES = 4
+# the Python reference cannot travel to the GPU box; measured where it can run (build container, 8 cores,
+# scripts/cpu_reference_vs_oracle.py, workload c2): reference 127 ms/step, this port 214 ms/step
+ORACLE_CALIBRATION = ("calibration: the unmodified torch-pme reference with 8 torch threads runs c2 1.7x faster "
+                      "than this port on the build container")
 
 
 def measured_peak():
@@ -211,7 +215,8 @@ def run_reference(args, wl):
     warmup = 1
     rate, sec = oracle_step_rate(wl, cpu, steps, warmup)
     cores = os.cpu_count()
-    sample = f"{steps} full steps of the workload after {warmup} warm-up (numpy/scipy oracle, scipy.fft workers=all cores)"
+    sample = (f"{steps} full steps of the workload after {warmup} warm-up (numpy/scipy oracle, scipy.fft workers=all "
+              f"cores; {ORACLE_CALIBRATION})")
     line = {
         "impl": "reference", "metric": "atom-steps/sec (energy+forces)", "value": rate, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
@@ -476,7 +481,8 @@ def run_b200(args, wl):
         rate, sec = oracle_step_rate(wl, cpu, n_cpu_steps, 1)
         cpu_baseline = {"value": rate, "unit": "atom-steps/s", "cores": os.cpu_count(), "kind": "port",
                         "sample": f"{n_cpu_steps} full step(s) of the same workload after 1 warm-up, numpy/scipy oracle "
-                                  f"({sec:.2f} s/step; scipy.fft on all cores, the rest single-threaded numpy)"}
+                                  f"({sec:.2f} s/step; scipy.fft on all cores, the rest single-threaded numpy; "
+                                  f"{ORACLE_CALIBRATION})"}
 
     if rank == 0:
         per_step = graph_ms / args.steps
