@@ -249,6 +249,34 @@ int tpme_pair_backward(int dtype, const void* charges, const void* neighbor_indi
                        const tpme_pair_potential* potential_host, void* grad_charges,
                        void* grad_pairs, void* stream);
 
+/* ---- EXPERIMENTAL: neighbor list on the GPU -------------------
+ * The reference takes the neighbor list from the external `vesin` package (tests/helpers.py:240-275,
+ * examples/basic-usage.py:166-169).  Cell-list search in two passes over atoms that the caller has
+ * wrapped into the cell, binned (slabs between lattice planes, `n_bins[a]` per direction) and sorted
+ * by bin:  wrapped (N,3) reals, wrap_shift (N,3) int32 (wrapped = r - wrap_shift . cell),
+ * atom_bins (N,3) int32, order (N) int32 (sorted slot -> atom), bin_start (prod(n_bins)+1) int32.
+ *   tpme_neighbor_count  counts[slot] = neighbors of the atom in sorted slot `slot`
+ *   tpme_neighbor_fill   with the exclusive scan `offsets` of the counts: indices (P,2) int64,
+ *                        squared distances (P), integer image shifts (P,3) w.r.t. the original positions
+ * A pair (i, j, S) is the image r_j + S . cell seen from r_i; half lists keep i < j (any S) and
+ * self images with S lexicographically positive.  Not yet validated on a GPU; the search loop
+ * itself (csrc/neighbors_core.h) is validated on the CPU by tests/test_neighbors.py. */
+typedef struct tpme_neighbor_search {
+  double cell[9];    /* host, row-major, rows = lattice vectors */
+  int n_bins[3];
+  int reach[3];      /* bins visited on each side: ceil(cutoff / slab thickness) */
+  int periodic[3];
+  int full_list;
+  double cutoff;
+} tpme_neighbor_search;
+int tpme_neighbor_count(int dtype, const void* wrapped, const int* wrap_shift, const int* atom_bins,
+                        const int* order, const int* bin_start, int64_t n_atoms,
+                        const tpme_neighbor_search* search_host, int* counts, void* stream);
+int tpme_neighbor_fill(int dtype, const void* wrapped, const int* wrap_shift, const int* atom_bins,
+                       const int* order, const int* bin_start, int64_t n_atoms,
+                       const tpme_neighbor_search* search_host, const int64_t* offsets,
+                       int64_t* indices, void* distances_sq, int* shifts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,3 +37,28 @@ def test_energy_and_gradients_matches_autograd(method, dtype):
     graphed.replay()
     torch.cuda.synchronize()
     assert rel_err(graphed.grad_positions, gp) < tol * 10 and rel_err(graphed.grad_distances, gd) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("full", [False, True])
+def test_gpu_neighbor_list_matches_oracle_and_feeds_the_calculator(full, dtype):
+    import numpy as np
+
+    import torchpme_b200 as tp
+    from oracle import pme_oracle as oracle
+    from torchpme_b200.neighbors import distances_from, neighbor_list
+
+    pos, q, cell, idx_ref, d_ref = rocksalt(6, dtype=torch.float64, device="cuda", cutoff=5.0)
+    idx, d, s = neighbor_list(pos.to(dtype), cell.to(dtype), 5.0, full_neighbor_list=full)
+    o_idx, o_d, o_s = oracle.neighbor_list(pos.cpu().numpy(), cell.cpu().numpy(), 5.0, full=full)
+    assert idx.shape[0] == o_idx.shape[0]
+    assert abs(float(d.double().sum()) - float(o_d.sum())) < 1e-4 * float(o_d.sum())
+    assert rel_err(d, distances_from(pos.to(dtype), cell.to(dtype), idx, s)) < (1e-12 if dtype == torch.float64 else 1e-5)
+    # the calculator gives the same potentials with this list as with the synthetic generator's
+    calc = tp.P3MCalculator(tp.CoulombPotential(smearing=1.0).to("cuda"), mesh_spacing=float(cell[0, 0]) / 14,
+                            full_neighbor_list=full)
+    V = calc(q.to(dtype), cell.to(dtype), pos.to(dtype), idx, d)
+    if not full:
+        V_ref = calc(q.to(dtype), cell.to(dtype), pos.to(dtype), idx_ref, d_ref.to(dtype))
+        assert rel_err(V, V_ref) < (1e-10 if dtype == torch.float64 else 1e-4)
+    assert np.isfinite(V.cpu().numpy()).all()

@@ -70,6 +70,17 @@ class _PointEpilogue(ctypes.Structure):
     ]
 
 
+class _NeighborSearch(ctypes.Structure):
+    _fields_ = [
+        ("cell", ctypes.c_double * 9),
+        ("n_bins", ctypes.c_int * 3),
+        ("reach", ctypes.c_int * 3),
+        ("periodic", ctypes.c_int * 3),
+        ("full_list", ctypes.c_int),
+        ("cutoff", ctypes.c_double),
+    ]
+
+
 class _SlabPeers(ctypes.Structure):
     _fields_ = [
         ("n_ranks", ctypes.c_int),
@@ -108,6 +119,9 @@ SIGNATURES = {
     "tpme_peer_buffer_close": ([_vp], _i),
     "tpme_peer_buffer_destroy": ([_vp], _i),
     "tpme_peer_barrier": ([ctypes.POINTER(_vp), _i, _i, _vp, ctypes.c_double, _vp, _vp], _i),
+    "tpme_neighbor_count": ([_i, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.POINTER(_NeighborSearch), _vp, _vp], _i),
+    "tpme_neighbor_fill": ([_i, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.POINTER(_NeighborSearch), _vp, _vp, _vp,
+                            _vp, _vp], _i),
     "tpme_peer_allreduce": ([_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i64, _vp], _i),
     "tpme_fft_plan_create": ([ctypes.POINTER(_vp), _i, _i, _i, _i, _i], _i),
     "tpme_fft_plan_destroy": ([_vp], _i),
