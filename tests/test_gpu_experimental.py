@@ -62,3 +62,31 @@ def test_gpu_neighbor_list_matches_oracle_and_feeds_the_calculator(full, dtype):
         V_ref = calc(q.to(dtype), cell.to(dtype), pos.to(dtype), idx_ref, d_ref.to(dtype))
         assert rel_err(V, V_ref) < (1e-10 if dtype == torch.float64 else 1e-4)
     assert np.isfinite(V.cpu().numpy()).all()
+
+
+def test_spline_and_combined_potentials_through_the_generic_routes():
+    """a spline of the smeared Coulomb potential reproduces CoulombPotential's long-range part"""
+    import math
+
+    import torchpme_b200 as tp
+
+    dt = torch.float64
+    pos, q, cell, idx, d = rocksalt(6, dtype=dt, device="cuda", cutoff=5.0)
+    smearing = 1.0
+    r = torch.logspace(-2, 2, 800, dtype=dt)
+    y = torch.erf(r / smearing / 2 ** 0.5) / r
+    spline = tp.SplinePotential(r, y, reciprocal=True, y_at_zero=math.sqrt(2 / math.pi) / smearing,
+                                yhat_at_zero=0.0, smearing=smearing).to("cuda")
+    coulomb = tp.CoulombPotential(smearing=smearing).to("cuda")
+    spacing = float(cell[0, 0]) / 14
+    v_spline = tp.PMECalculator(spline, mesh_spacing=spacing)._compute_kspace(q, cell, pos)
+    v_coulomb = tp.PMECalculator(coulomb, mesh_spacing=spacing)._compute_kspace(q, cell, pos)
+    assert rel_err(v_spline, v_coulomb) < 1e-3
+    combined = tp.CombinedPotential([coulomb, tp.InversePowerLawPotential(exponent=4, smearing=smearing).to("cuda")],
+                                    initial_weights=torch.tensor([1.0, 0.0], dtype=dt), smearing=smearing).to("cuda")
+    p = pos.clone().requires_grad_(True)
+    V = tp.PMECalculator(combined, mesh_spacing=spacing)(q, cell, p, idx, d)
+    V_ref = tp.PMECalculator(coulomb, mesh_spacing=spacing)(q, cell, pos, idx, d)
+    assert rel_err(V.detach(), V_ref) < 1e-9
+    (V * q).sum().backward()
+    assert combined.weights.grad is not None and p.grad is not None

@@ -1,0 +1,138 @@
+"""
+``SplinePotential`` / ``CombinedPotential`` and the spline library: host-side interface code in plain
+torch ops, checked on the CPU against the unmodified reference where
+it can be imported (build container) and against closed forms everywhere.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import torchpme_b200 as tp
+from torchpme_b200 import splines
+
+try:
+    from _reference_import import available, import_reference
+    HAVE_REF = available()
+except Exception:  # pragma: no cover
+    HAVE_REF = False
+needs_reference = pytest.mark.skipif(not HAVE_REF, reason="reference tree not present (GPU box)")
+
+
+def test_natural_spline_reproduces_cubics_and_is_smooth():
+    x = torch.linspace(0.0, 4.0, 60, dtype=torch.float64)
+    y = torch.sin(x)
+    sp = splines.CubicSpline(x, y)
+    q = torch.linspace(0.05, 3.95, 300, dtype=torch.float64)
+    assert float((sp(q) - torch.sin(q)).abs().max()) < 2e-4       # natural ends: sin'' != 0 at x = 4
+    inner = (q > 0.5) & (q < 3.5)
+    assert float((sp(q) - torch.sin(q)).abs()[inner].max()) < 5e-6
+    assert float(sp.d2y_points[0]) == 0.0 and float(sp.d2y_points[-1]) == 0.0
+    np.testing.assert_allclose(sp(x).numpy(), y.numpy(), rtol=0, atol=1e-14)          # interpolates
+    # a straight line has zero second derivatives and is continued linearly outside the grid
+    line = splines.CubicSpline(x, 2 * x + 1)
+    np.testing.assert_allclose(line(torch.tensor([-1.0, 5.0], dtype=torch.float64)).numpy(), [-1.0, 11.0], atol=1e-12)
+    # differentiable in the evaluation points
+    q.requires_grad_(True)
+    (g,) = torch.autograd.grad(sp(q).sum(), q)
+    assert float((g - torch.cos(q)).abs()[inner].max()) < 5e-4
+
+
+def test_spline_fourier_transform_of_a_gaussian():
+    """4 pi int sin(kr)/k r exp(-r^2/2) dr = (2 pi)^(3/2) exp(-k^2/2)"""
+    r = torch.linspace(0.0, 12.0, 600, dtype=torch.float64)
+    f = torch.exp(-0.5 * r * r)
+    k = torch.linspace(0.0, 6.0, 25, dtype=torch.float64)
+    ft = splines.compute_spline_ft(k, r, f, splines.compute_second_derivatives(r, f))
+    exact = (2 * math.pi) ** 1.5 * torch.exp(-0.5 * k * k)
+    assert float((ft - exact).abs().max() / exact.max()) < 2e-7
+
+
+@needs_reference
+def test_spline_library_matches_reference():
+    import_reference()
+    from torchpme.lib import splines as ref
+
+    gen = torch.Generator().manual_seed(0)
+    x = torch.sort(torch.rand(40, generator=gen, dtype=torch.float64) * 9 + 0.05).values
+    y = torch.exp(-0.3 * x) * torch.cos(x)
+    q = torch.rand(300, generator=gen, dtype=torch.float64) * 12 - 1
+    np.testing.assert_allclose(splines.compute_second_derivatives(x, y).numpy(),
+                               ref.compute_second_derivatives(x, y).numpy(), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(splines.CubicSpline(x, y)(q).numpy(), ref.CubicSpline(x, y)(q).numpy(),
+                               rtol=1e-11, atol=1e-13)
+    for y0 in (None, 2.0):
+        np.testing.assert_allclose(splines.CubicSplineReciprocal(x, y, y_at_zero=y0)(q.abs()).numpy(),
+                                   ref.CubicSplineReciprocal(x, y, y_at_zero=y0)(q.abs()).numpy(),
+                                   rtol=1e-11, atol=1e-13)
+    r = torch.logspace(-2, 2, 400, dtype=torch.float64)
+    f = torch.erf(r / 1.2 / 2 ** 0.5) / r
+    k = torch.cat([torch.zeros(1, dtype=torch.float64), 2 * torch.pi / r.flip(0)])
+    mine = splines.compute_spline_ft(k, r, f, splines.compute_second_derivatives(r, f))
+    theirs = ref.compute_spline_ft(k, r, f, ref.compute_second_derivatives(r, f))
+    assert float((mine - theirs).abs().max() / theirs.abs().max()) < 1e-12
+    # pointwise, except where the transform has decayed to ~1e-8 of its maximum (cancellation in both)
+    big = theirs.abs() > 1e-6 * theirs.abs().max()
+    assert float(((mine - theirs).abs() / theirs.abs())[big].max()) < 1e-8
+
+
+@needs_reference
+@pytest.mark.parametrize("reciprocal", [False, True])
+def test_spline_potential_matches_reference(reciprocal):
+    ref = import_reference()
+    r = torch.logspace(-2, 2, 300, dtype=torch.float64)
+    y = torch.erf(r / 1.0 / 2 ** 0.5) / r
+    kw = dict(reciprocal=reciprocal, smearing=1.0, prefactor=1.3)
+    if reciprocal:
+        kw.update(y_at_zero=math.sqrt(2 / math.pi), yhat_at_zero=0.0)
+    mine, theirs = tp.SplinePotential(r, y, **kw), ref.SplinePotential(r, y, **kw)
+    np.testing.assert_allclose(mine.yhat_grid.numpy(), theirs.yhat_grid.numpy(), rtol=1e-7,
+                               atol=1e-12 * float(theirs.yhat_grid.abs().max()))
+    d = torch.rand(200, dtype=torch.float64) * 20 + 0.005
+    k_sq = torch.rand(200, dtype=torch.float64) * 50
+    for fn, arg in (("lr_from_dist", d), ("from_dist", d), ("sr_from_dist", d), ("lr_from_k_sq", k_sq)):
+        a, b = getattr(mine, fn)(arg), getattr(theirs, fn)(arg)
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-7, atol=1e-10, err_msg=fn)
+    np.testing.assert_allclose(mine.self_contribution().numpy(), theirs.self_contribution().numpy(), rtol=1e-10)
+    assert float(mine.background_correction().abs().sum()) == 0.0
+    assert mine._native_descriptor() is None                    # served by the generic routes
+
+
+@needs_reference
+def test_combined_potential_matches_reference():
+    ref = import_reference()
+    d = torch.rand(100, dtype=torch.float64) * 6 + 0.2
+    k_sq = torch.rand(100, dtype=torch.float64) * 30
+    w = torch.tensor([0.7, -1.9], dtype=torch.float64)
+    mine = tp.CombinedPotential([tp.CoulombPotential(smearing=1.1), tp.InversePowerLawPotential(exponent=4, smearing=1.1)],
+                                initial_weights=w.clone(), smearing=1.1)
+    theirs = ref.CombinedPotential([ref.CoulombPotential(smearing=1.1), ref.InversePowerLawPotential(exponent=4, smearing=1.1)],
+                                   initial_weights=w.clone(), smearing=1.1)
+    for fn, arg in (("from_dist", d), ("sr_from_dist", d), ("lr_from_dist", d), ("lr_from_k_sq", k_sq)):
+        np.testing.assert_allclose(getattr(mine, fn)(arg).detach().numpy(), getattr(theirs, fn)(arg).detach().numpy(),
+                                   rtol=1e-11, atol=1e-13, err_msg=fn)
+    for fn in ("self_contribution", "background_correction"):
+        np.testing.assert_allclose(getattr(mine, fn)().detach().numpy(), getattr(theirs, fn)().detach().numpy(), rtol=1e-12)
+    # the weights are trainable parameters by default
+    assert isinstance(mine.weights, torch.nn.Parameter)
+    mine.lr_from_dist(d).sum().backward()
+    assert mine.weights.grad is not None and mine.weights.grad.shape == (2,)
+    fixed = tp.CombinedPotential([tp.CoulombPotential(smearing=1.0)], learnable_weights=False, smearing=1.0)
+    assert not isinstance(fixed.weights, torch.nn.Parameter)
+
+
+def test_combined_potential_argument_errors():
+    direct, ranged = tp.CoulombPotential(), tp.CoulombPotential(smearing=1.0)
+    with pytest.raises(ValueError, match="Cannot combine direct"):
+        tp.CombinedPotential([direct, ranged], smearing=1.0)
+    with pytest.raises(ValueError, match="You should specify a `smearing`"):
+        tp.CombinedPotential([ranged, ranged])
+    with pytest.raises(ValueError, match="Cannot specify `smearing` when combining direct"):
+        tp.CombinedPotential([direct, direct], smearing=1.0)
+    with pytest.raises(ValueError, match="number of initial weights must match"):
+        tp.CombinedPotential([ranged, ranged], initial_weights=torch.ones(3), smearing=1.0)
+    with pytest.raises(ValueError, match="Length of radial grid and value array mismatch"):
+        tp.SplinePotential(torch.linspace(0.1, 1, 5), torch.ones(4))
+    with pytest.raises(ValueError, match="Positive-valued radial grid"):
+        tp.SplinePotential(torch.linspace(0.0, 1, 5), torch.ones(5), reciprocal=True)

@@ -16,7 +16,8 @@ from ._native import NativeLibraryError, library_path  # noqa: F401
 from .calculators import Calculator, P3MCalculator, PMECalculator
 from .graphs import GraphedStep  # noqa: F401
 from .mesh import set_nan_check  # noqa: F401
-from .potentials import CoulombPotential, InversePowerLawPotential, Potential
+from .potentials import (CombinedPotential, CoulombPotential, InversePowerLawPotential, Potential,
+                         SplinePotential)
 
 __version__ = "0.1.0"
 __all__ = [
@@ -25,5 +26,7 @@ __all__ = [
     "PMECalculator",
     "CoulombPotential",
     "InversePowerLawPotential",
+    "SplinePotential",
+    "CombinedPotential",
     "Potential",
 ]

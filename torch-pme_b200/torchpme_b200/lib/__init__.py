@@ -8,3 +8,9 @@ from ..mesh import (  # noqa: F401
     get_ns_mesh,
 )
 from ..potentials import exp1, gamma, gammaincc_over_powerlaw  # noqa: F401
+from ..splines import (  # noqa: F401
+    CubicSpline,
+    CubicSplineReciprocal,
+    compute_second_derivatives,
+    compute_spline_ft,
+)

@@ -274,3 +274,128 @@ class InversePowerLawPotential(Potential):
         if self._p == 1:
             return self.prefactor * _slab_correction(periodic, positions, cell, charges)
         return super().pbc_correction(periodic, positions, cell, charges)
+
+
+class SplinePotential(Potential):
+    """
+    Tabulated potential: a cubic spline of ``(r_grid, y_grid)`` in real space and of
+    ``(k_grid^2, yhat_grid)`` in reciprocal space, the latter computed from the former when not
+    given (reference: ``potentials/spline.py:12-169``).  Purely long-ranged by default
+    (``sr_from_dist`` is zero); on the calculators it is served by the generic routes (per-pair
+    values and a filter table built from these torch functions).
+    """
+
+    def __init__(self, r_grid: torch.Tensor, y_grid: torch.Tensor, k_grid=None, yhat_grid=None,
+                 reciprocal: bool = False, y_at_zero=None, yhat_at_zero=None, smearing=None,
+                 exclusion_radius=None, exclusion_degree: int = 1, prefactor: float = 1.0):
+        super().__init__(smearing, exclusion_radius, exclusion_degree, prefactor)
+        from .splines import CubicSpline, CubicSplineReciprocal, compute_second_derivatives, compute_spline_ft
+
+        if len(y_grid) != len(r_grid):
+            raise ValueError("Length of radial grid and value array mismatch.")
+        if reciprocal and torch.min(r_grid) <= 0.0:
+            raise ValueError("Positive-valued radial grid is needed for reciprocal axis spline.")
+        self.register_buffer("r_grid", r_grid)
+        self.register_buffer("y_grid", y_grid)
+        self._reciprocal = bool(reciprocal)
+        if k_grid is None:
+            # 2 pi / r (ascending) on a reciprocal axis, the radial grid itself otherwise
+            k_grid = 2 * torch.pi / r_grid.flip(0) if reciprocal else r_grid.detach().clone()
+        self.register_buffer("k_grid", k_grid)
+        if yhat_grid is None:
+            yhat_grid = compute_spline_ft(k_grid, r_grid, y_grid, compute_second_derivatives(r_grid, y_grid))
+        self.register_buffer("yhat_grid", yhat_grid)
+        self._y_at_zero_arg, self._yhat_at_zero_arg = y_at_zero, yhat_at_zero
+        self._build = (CubicSpline, CubicSplineReciprocal)
+        self._splines_for = None
+
+    def _splines(self):
+        """the spline objects, rebuilt when the buffers moved (``.to(device / dtype)``)"""
+        key = (self.r_grid.device, self.r_grid.dtype, self.r_grid.data_ptr(), self.yhat_grid.data_ptr())
+        if self._splines_for != key:
+            plain, recip = self._build
+            if self._reciprocal:
+                self._spline = recip(self.r_grid, self.y_grid, y_at_zero=self._y_at_zero_arg)
+                self._krn_spline = recip(self.k_grid**2, self.yhat_grid, y_at_zero=self._yhat_at_zero_arg)
+            else:
+                self._spline = plain(self.r_grid, self.y_grid)
+                self._krn_spline = plain(self.k_grid**2, self.yhat_grid)
+            zero = torch.zeros(1, dtype=self.r_grid.dtype, device=self.r_grid.device)
+            self._y_at_zero = self._spline(zero) if self._y_at_zero_arg is None else \
+                torch.as_tensor(self._y_at_zero_arg, dtype=zero.dtype, device=zero.device)
+            self._yhat_at_zero = self._krn_spline(zero) if self._yhat_at_zero_arg is None else \
+                torch.as_tensor(self._yhat_at_zero_arg, dtype=zero.dtype, device=zero.device)
+            self._splines_for = key
+        return self._spline, self._krn_spline
+
+    def from_dist(self, dist, pair_mask=None):
+        # as in the reference: the prefactor multiplies the (already scaled) long-range part again
+        return self.prefactor * (self.lr_from_dist(dist, pair_mask) + self.sr_from_dist(dist, pair_mask))
+
+    def sr_from_dist(self, dist, pair_mask=None):
+        return 0.0 * dist
+
+    def lr_from_dist(self, dist, pair_mask=None):
+        return self.prefactor * self._splines()[0](dist)
+
+    def lr_from_k_sq(self, k_sq):
+        return self.prefactor * self._splines()[1](k_sq)
+
+    def self_contribution(self):
+        self._splines()
+        return self.prefactor * self._y_at_zero
+
+    def background_correction(self):
+        return self.prefactor * torch.zeros(1, dtype=self.prefactor.dtype, device=self.prefactor.device)
+
+
+class CombinedPotential(Potential):
+    """
+    Weighted sum of potentials, with fixed or trainable weights (reference:
+    ``potentials/combined.py:6-124``).  All members must be range separated (then ``smearing`` is
+    required) or all direct (then it must be omitted).
+    """
+
+    def __init__(self, potentials, initial_weights=None, learnable_weights: bool = True, smearing=None,
+                 exclusion_radius=None, exclusion_degree: int = 1):
+        super().__init__(smearing=smearing, exclusion_radius=exclusion_radius, exclusion_degree=exclusion_degree)
+        has_smearing = [pot.smearing is not None and bool(pot.smearing) for pot in potentials]
+        if any(has_smearing) and not all(has_smearing):
+            raise ValueError(
+                "Cannot combine direct (`smearing=None`) and range-separated (`smearing=float`) potentials.")
+        if all(has_smearing) and not self.smearing:
+            raise ValueError(
+                "You should specify a `smearing` when combining range-separated (`smearing=float`) potentials.")
+        if not any(has_smearing) and self.smearing:
+            raise ValueError("Cannot specify `smearing` when combining direct (`smearing=None`) potentials.")
+        if initial_weights is None:
+            initial_weights = torch.ones(len(potentials))
+        elif len(initial_weights) != len(potentials):
+            raise ValueError("The number of initial weights must match the number of potentials being combined")
+        self.potentials = torch.nn.ModuleList(potentials)
+        if learnable_weights:
+            self.weights = torch.nn.Parameter(initial_weights)
+        else:
+            self.register_buffer("weights", initial_weights)
+
+    def _mix(self, parts):
+        stacked = torch.stack([p.to(self.weights.dtype) if p.dtype != self.weights.dtype else p for p in parts], dim=-1)
+        return torch.inner(self.weights.to(stacked.dtype), stacked)
+
+    def from_dist(self, dist, pair_mask=None):
+        return self._mix([pot.from_dist(dist, pair_mask) for pot in self.potentials])
+
+    def sr_from_dist(self, dist, pair_mask=None):
+        return self._mix([pot.sr_from_dist(dist, pair_mask) for pot in self.potentials])
+
+    def lr_from_dist(self, dist, pair_mask=None):
+        return self._mix([pot.lr_from_dist(dist, pair_mask) for pot in self.potentials])
+
+    def lr_from_k_sq(self, k_sq):
+        return self._mix([pot.lr_from_k_sq(k_sq) for pot in self.potentials])
+
+    def self_contribution(self):
+        return self._mix([pot.self_contribution().reshape(()) for pot in self.potentials])
+
+    def background_correction(self):
+        return self._mix([pot.background_correction().reshape(()) for pot in self.potentials])
