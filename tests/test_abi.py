@@ -63,3 +63,43 @@ def test_cpu_tensors_fail_loudly():
     calc = tp.PMECalculator(tp.CoulombPotential(smearing=0.5), mesh_spacing=0.25)
     with pytest.raises(tp.NativeLibraryError, match="CUDA-only"):
         calc(torch.ones(2, 1), torch.eye(3), torch.rand(2, 3), torch.tensor([[0, 1]]), torch.tensor([0.5]))
+
+
+def test_slab_and_peer_entry_points_validate_arguments_without_a_gpu():
+    """host-side argument checks of the multi-GPU entry points run before any CUDA call"""
+    from torchpme_b200 import _native
+
+    lib = _native.load()
+    err = lambda: lib.tpme_last_error().decode()  # noqa: E731
+    r2u = (ctypes.c_double * 9)()
+    # slab outside the mesh
+    assert lib.tpme_spread_slab(0, None, None, 1, 1, r2u, 8, 8, 8, 6, 4, None, None, 4, 0, None, 0, None) != 0
+    assert "slab" in err()
+    # a point list without its length
+    dummy = ctypes.c_void_p(16)
+    assert lib.tpme_gather_slab(0, dummy, dummy, 1, 1, r2u, 8, 8, 8, 0, 8, dummy, None, 4, 0, dummy, None, None,
+                                None) != 0
+    assert "go together" in err()
+    # non-power-of-two meshes are refused by the slab FFT pieces
+    assert lib.tpme_slab_fft_yz(0, 1, dummy, dummy, 4, 12, 16, None) != 0 and "power-of-two" in err()
+    green = _native.make_green(1, 1.0, [0.0] * 9)
+    assert lib.tpme_slab_fft_x_green(0, dummy, 1, 16, 16, 16, 12, 8, ctypes.byref(green), None) != 0
+    assert "y slab" in err()
+    # exchange copy: element size and rank count
+    ptrs = (ctypes.c_void_p * 1)(16)
+    assert lib.tpme_slab_exchange_copy(4, dummy, ptrs, 1, 1, 1, 8, 0, 0, 0, 0, 0, None) != 0 and "complex" in err()
+    assert lib.tpme_slab_exchange_copy(8, dummy, ptrs, 1, 99, 1, 8, 0, 0, 0, 0, 0, None) != 0 and "destinations" in err()
+    # peers: world size must divide the mesh, buffers must be present
+    peers = _native.make_slab_peers(0, [16, 32, 48], [16, 32, 48])
+    assert lib.tpme_slab_fft_yz_push(0, dummy, 1, 16, 16, 16, ctypes.byref(peers), None) != 0 and "divide" in err()
+    peers = _native.make_slab_peers(0, [16, 0], [16, 32])
+    assert lib.tpme_slab_fft_yz_push(0, dummy, 1, 16, 16, 16, ctypes.byref(peers), None) != 0 and "null peer" in err()
+    # all-reduce: alignment and rank layout
+    a = (ctypes.c_void_p * 2)(16, 40)
+    assert lib.tpme_peer_allreduce(0, a, a, 2, 0, 64, None) != 0 and "aligned" in err()
+    assert lib.tpme_peer_allreduce(0, a, a, 2, 5, 64, None) != 0 and "rank layout" in err()
+    assert lib.tpme_peer_barrier(a, 0, 0, dummy, 1.0, dummy, None) != 0 and "rank layout" in err()
+    # neighbor search parameters
+    search = _native._NeighborSearch()
+    assert lib.tpme_neighbor_count(0, dummy, dummy, dummy, dummy, dummy, 4, ctypes.byref(search), dummy, None) != 0
+    assert "cutoff" in err()
