@@ -136,3 +136,32 @@ def test_combined_potential_argument_errors():
         tp.SplinePotential(torch.linspace(0.1, 1, 5), torch.ones(4))
     with pytest.raises(ValueError, match="Positive-valued radial grid"):
         tp.SplinePotential(torch.linspace(0.0, 1, 5), torch.ones(5), reciprocal=True)
+
+
+@needs_reference
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_p3m_filter_tables_match_reference(mode):
+    """P3MKSpaceFilter's influence-function table (torch ops; modes 1-3 only exist as tables)"""
+    ref = import_reference()
+    gen = torch.Generator().manual_seed(mode)
+    cell = torch.eye(3, dtype=torch.float64) * 6.0 + 0.5 * torch.rand(3, 3, generator=gen, dtype=torch.float64)
+    ns = torch.tensor([6, 8, 5])
+    for order in (1, 2, 4, 6):
+        for nodes in (2, 4):
+            mine = tp.lib.P3MKSpaceFilter(cell, ns, nodes, tp.CoulombPotential(smearing=0.9), mode=mode,
+                                          differential_order=order, fft_norm="backward", ifft_norm="forward")
+            # the reference registers its finite-difference coefficients after the first update(), so
+            # modes 1-3 cannot be constructed directly: build with mode 0, switch, update again
+            theirs = ref.lib.P3MKSpaceFilter(cell, ns, nodes, ref.CoulombPotential(smearing=0.9), mode=0,
+                                             differential_order=order, fft_norm="backward", ifft_norm="forward")
+            theirs.mode = mode
+            theirs.update(cell, ns)
+            # the reference keeps the finite-difference coefficients (4/3, -1/3, ...) in a float32 buffer
+            # even for float64 meshes: agreement is limited to ~1e-7 per power of the operator there
+            tol = 1e-10 if (mode == 0 or order == 1) else 5e-6
+            np.testing.assert_allclose(mine._kfilter.numpy(), theirs._kfilter.numpy(), rtol=tol, atol=1e-13,
+                                       err_msg=f"mode {mode} order {order} nodes {nodes}")
+    with pytest.raises(ValueError, match=r"`mode` should be one of \[0, 1, 2, 3\], but got 4"):
+        tp.lib.P3MKSpaceFilter(cell, ns, 4, tp.CoulombPotential(smearing=0.9), mode=4)
+    with pytest.raises(ValueError, match="`differential_order` should be one between 1 and 6, but got 7"):
+        tp.lib.P3MKSpaceFilter(cell, ns, 4, tp.CoulombPotential(smearing=0.9), differential_order=7)
