@@ -165,3 +165,32 @@ def test_p3m_filter_tables_match_reference(mode):
         tp.lib.P3MKSpaceFilter(cell, ns, 4, tp.CoulombPotential(smearing=0.9), mode=4)
     with pytest.raises(ValueError, match="`differential_order` should be one between 1 and 6, but got 7"):
         tp.lib.P3MKSpaceFilter(cell, ns, 4, tp.CoulombPotential(smearing=0.9), differential_order=7)
+
+
+@needs_reference
+def test_potential_interface_matches_live_reference():
+    """torch side of Coulomb / inverse-power-law potentials, incl. the 2-D slab term, vs the reference"""
+    ref = import_reference()
+    gen = torch.Generator().manual_seed(9)
+    d = torch.rand(64, generator=gen, dtype=torch.float64) * 5 + 0.3
+    k_sq = torch.cat([torch.zeros(1, dtype=torch.float64), torch.rand(64, generator=gen, dtype=torch.float64) * 40])
+    mask = torch.rand(64, generator=gen) < 0.7
+    pos = torch.rand(7, 3, generator=gen, dtype=torch.float64) * 4
+    cell = torch.eye(3, dtype=torch.float64) * 4 + 0.3 * torch.rand(3, 3, generator=gen, dtype=torch.float64)
+    q = torch.randn(7, 2, generator=gen, dtype=torch.float64)
+    pairs = [(tp.CoulombPotential(smearing=0.8, exclusion_radius=2.5, exclusion_degree=2, prefactor=1.4),
+              ref.CoulombPotential(smearing=0.8, exclusion_radius=2.5, exclusion_degree=2, prefactor=1.4))]
+    for p in range(1, 7):
+        pairs.append((tp.InversePowerLawPotential(exponent=p, smearing=0.8, prefactor=0.6),
+                      ref.InversePowerLawPotential(exponent=p, smearing=0.8, prefactor=0.6)))
+    for mine, theirs in pairs:
+        for fn, args in (("from_dist", (d,)), ("from_dist", (d, mask)), ("lr_from_dist", (d,)), ("sr_from_dist", (d,)),
+                         ("sr_from_dist", (d, mask)), ("lr_from_k_sq", (k_sq,)), ("kernel_from_k_sq", (k_sq,)),
+                         ("self_contribution", ()), ("background_correction", ())):
+            a, b = getattr(mine, fn)(*args), getattr(theirs, fn)(*args)
+            np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-10, atol=1e-14, err_msg=f"{type(mine).__name__} {fn}")
+        for periodic in ([True, True, False], [True, False, True], [False, True, True], [True, True, True]):
+            per = torch.tensor(periodic)
+            np.testing.assert_allclose(mine.pbc_correction(per, pos, cell, q).numpy(),
+                                       theirs.pbc_correction(per, pos, cell, q).numpy(), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(pairs[0][0].f_cutoff(d).numpy(), pairs[0][1].f_cutoff(d).numpy(), rtol=1e-13)
