@@ -4,6 +4,7 @@ from ..mesh import (  # noqa: F401
     KSpaceKernel,
     MeshInterpolator,
     P3MKSpaceFilter,
+    generate_kvectors_for_ewald,
     generate_kvectors_for_mesh,
     get_ns_mesh,
 )
@@ -14,3 +15,4 @@ from ..splines import (  # noqa: F401
     compute_second_derivatives,
     compute_spline_ft,
 )
+from . import kspace_filter, kvectors, math, mesh_interpolator, splines  # noqa: F401,E402

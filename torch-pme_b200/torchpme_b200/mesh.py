@@ -95,14 +95,31 @@ def generate_kvectors_for_mesh(cell: torch.Tensor, ns: torch.Tensor) -> torch.Te
     return _kvectors(cell, (nx, ny, nz))
 
 
-def _kvectors(cell, ns):
+def generate_kvectors_for_ewald(cell: torch.Tensor, ns: torch.Tensor) -> torch.Tensor:
+    """
+    All reciprocal vectors of the ``(nx, ny, nz)`` grid as an ``(nx ny nz, 3)`` tensor (full frequency
+    range along z; reference: lib/kvectors.py:24-74,104-130).  Utility only: the Ewald calculator
+    that consumes it is not part of this package.
+    """
+    if cell.shape != (3, 3):
+        raise ValueError(f"cell of shape {list(cell.shape)} should be of shape (3, 3)")
+    if ns.shape != (3,):
+        raise ValueError(f"ns of shape {list(ns.shape)} should be of shape (3, )")
+    if ns.device != cell.device:
+        raise ValueError(
+            f"`ns` and `cell` are not on the same device, got {ns.device} and {cell.device}."
+        )
+    return _kvectors(cell, _host_ints(ns), half_z=False).reshape(-1, 3)
+
+
+def _kvectors(cell, ns, half_z: bool = True):
     nx, ny, nz = ns
     inv = torch.linalg.inv_ex(cell)[0] if cell.is_cuda else torch.linalg.inv(cell)
     recip = 2 * torch.pi * inv.T
     opts = dict(device=cell.device, dtype=cell.dtype)
     fx = torch.fft.fftfreq(nx, **opts) * nx
     fy = torch.fft.fftfreq(ny, **opts) * ny
-    fz = torch.fft.rfftfreq(nz, **opts) * nz
+    fz = (torch.fft.rfftfreq(nz, **opts) if half_z else torch.fft.fftfreq(nz, **opts)) * nz
     return (fx[:, None, None, None] * recip[0]
             + fy[None, :, None, None] * recip[1]
             + fz[None, None, :, None] * recip[2])

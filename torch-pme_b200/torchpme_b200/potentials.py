@@ -346,7 +346,8 @@ class SplinePotential(Potential):
         return self.prefactor * self._y_at_zero
 
     def background_correction(self):
-        return self.prefactor * torch.zeros(1, dtype=self.prefactor.dtype, device=self.prefactor.device)
+        # (1,) tensor of the default dtype, like the reference's ``prefactor * torch.zeros(1)``
+        return self.prefactor * torch.zeros(1, device=self.prefactor.device)
 
 
 class CombinedPotential(Potential):

@@ -98,7 +98,8 @@ def compute_spline_ft(k_points: torch.Tensor, x_points: torch.Tensor, y_points: 
     Radial Fourier transform ``4 pi int sin(kr)/k r f(r) dr`` of the cubic spline
     ``(x_points, y_points, d2y_points)`` at ``k_points``, tail beyond the last point included (see the
     module docstring).  Evaluated once at construction time, in float64 numpy (needs ``scipy`` for
-    the cosine integral).
+    the cosine integral) whatever the dtype of the grids -- the reference evaluates in the grids'
+    dtype and loses accuracy for float32 grids (its tests/lib/test_splines.py:60-95 expects that).
     """
     try:
         from scipy.special import sici
