@@ -105,6 +105,40 @@ int tpme_slab_select_points(int dtype, const void* positions, int64_t n_points,
                             const double* r2u_host, int nx, int ny, int nz, int x0, int nx_local,
                             int nodes, int* point_list, int* list_count, void* stream);
 
+/* ---- tiled mesh interpolation: cell-sorted atoms + shared-memory mesh tiles moved by TMA bulk copies ----
+ * Same operations as tpme_spread / tpme_gather / tpme_gather_vjp (mesh_interpolator.py:303-457) for
+ * power-of-two meshes and 4 interpolation nodes.  tpme_tile_plan_make chooses the tiling (returns 3 when
+ * the mesh / stencil is not covered: use the direct calls); tpme_tile_sort bins the points once per set
+ * of positions; the spread accumulates a pencil of the mesh in shared memory and flushes it with
+ * cp.reduce.async.bulk, the gather stages the pencil with cp.async.bulk behind an mbarrier.
+ * Workspace (device, caller-allocated): bin_count (n_bins) int32, bin_start (n_bins + 1) int32,
+ * key_rank (2 N) int32 8-byte aligned, sorted_rec (4 N) reals 16-byte aligned, sorted_idx (N) int32. */
+typedef struct tpme_tile_plan {
+  int nx, ny, nz, nodes;
+  int tx, ty, zw;             /* pencil footprint (first stencil nodes) and z chunk width */
+  int npx, npy, nzc;          /* pencils per axis, z chunks per pencil */
+  int n_bins;                 /* npx * npy * nzc */
+  int row_stride, plane_stride; /* shared-memory tile strides in elements */
+  int smem_bytes;
+  int spread_threads, gather_threads;
+  int spread_batch;            /* atoms a warp of the spread fetches and stages at a time (16 or 32) */
+} tpme_tile_plan;
+int tpme_tile_plan_make(int dtype, int nx, int ny, int nz, int nodes, int method, int64_t n_points,
+                        tpme_tile_plan* plan_host);
+int tpme_tile_sort(int dtype, const tpme_tile_plan* plan_host, const void* positions, int64_t n_points,
+                   const double* r2u_host, int* bin_count, int* bin_start, int* key_rank,
+                   void* sorted_rec, int* sorted_idx, void* stream);
+int tpme_tile_spread(int dtype, const tpme_tile_plan* plan_host, const void* sorted_rec,
+                     const int* sorted_idx, const int* bin_start, const void* weights, int64_t n_points,
+                     int n_channels, int method, void* mesh, int accumulate, void* stream);
+/* values / dvalues / grad_positions (+ grad_r2u) select the outputs as in tpme_gather / tpme_gather_vjp
+ * (`coef`, `positions` only needed for grad_positions / grad_r2u) */
+int tpme_tile_gather(int dtype, const tpme_tile_plan* plan_host, const void* mesh, const void* sorted_rec,
+                     const int* sorted_idx, const int* bin_start, const void* positions, const void* coef,
+                     int64_t n_points, int n_channels, const double* r2u_host, int method, void* values,
+                     void* dvalues, void* grad_positions, int accumulate, void* grad_r2u,
+                     const tpme_point_epilogue* epilogue, void* stream);
+
 /* ---- reciprocal space ---------------------------------------------------------------
  * replaces KSpaceFilter.update + forward and P3MKSpaceFilter
  * (src/torchpme/lib/kspace_filter.py:97-120, 122-197, 293-329),

@@ -10,7 +10,11 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = "/root/reference/src"
+# the read-only tree in the build container, else the copy `oracle/make_ref.sh` made of it (which
+# travels to the GPU box; see __graft_entry__.build)
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = ("/root/reference/src", os.path.join(os.path.dirname(os.path.dirname(_HERE)), "oracle", "_ref"))
+REFERENCE_SRC = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "torchpme"))), _CANDIDATES[0])
 
 
 def available() -> bool:

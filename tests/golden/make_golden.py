@@ -90,6 +90,21 @@ add_case("rand_pme_larger", system="random", seed=902, n_atoms=200, n_channels=3
          full=True, box=11.0)
 
 
+# 2-D periodic systems (the slab correction of potentials/coulomb.py:6-40, applied at
+# calculators/pme.py:138-140): separate fixture file `periodic_cases.npz`
+PERIODIC_CASES = [
+    dict(name="slab_pme_xy", system="random", seed=950, n_atoms=24, n_channels=1, triclinic=False, calc="pme",
+         nodes=4, pot=dict(kind="coulomb", smearing=0.9), mesh_spacing=0.8, cutoff=3.1, full=False,
+         periodic=[True, True, False]),
+    dict(name="slab_p3m_xz", system="random", seed=951, n_atoms=30, n_channels=2, triclinic=False, calc="p3m",
+         nodes=4, pot=dict(kind="coulomb", smearing=1.0, prefactor=1.3), mesh_spacing=0.9, cutoff=3.3, full=True,
+         periodic=[True, False, True]),
+    dict(name="slab_pme_n5_yz", system="random", seed=952, n_atoms=20, n_channels=1, triclinic=False, calc="pme",
+         nodes=5, pot=dict(kind="coulomb", smearing=0.9), mesh_spacing=0.8, cutoff=3.1, full=False,
+         periodic=[False, True, True]),
+]
+
+
 def run_calc_case(case):
     if case["system"] == "cscl":
         pos = np.array([[0, 0, 0], [0.5, 0.5, 0.5]], dtype=np.float64)
@@ -109,7 +124,8 @@ def run_calc_case(case):
     t_cell = torch.tensor(cell, dtype=F64, requires_grad=True)
     t_d = torch.tensor(d, dtype=F64, requires_grad=True)
     t_idx = torch.tensor(idx)
-    V = calc.forward(t_q, t_cell, t_pos, t_idx, t_d)
+    periodic = torch.tensor(case["periodic"]) if "periodic" in case else None
+    V = calc.forward(t_q, t_cell, t_pos, t_idx, t_d, periodic=periodic)
     # a generic upstream gradient (not equal to the charges) exercises the full backward
     rng = np.random.default_rng(7)
     g = torch.tensor(rng.normal(size=q.shape), dtype=F64)
@@ -123,7 +139,7 @@ def run_calc_case(case):
     # energy-style backward, L = sum q V (the benchmark step)
     for t in (t_pos, t_q, t_cell, t_d):
         t.grad = None
-    V2 = calc.forward(t_q, t_cell, t_pos, t_idx, t_d)
+    V2 = calc.forward(t_q, t_cell, t_pos, t_idx, t_d, periodic=periodic)
     (V2 * t_q.detach()).sum().backward()
     out.update(dpos_energy=t_pos.grad.numpy(), dd_energy=t_d.grad.numpy(), dcell_energy=t_cell.grad.numpy())
     return out
@@ -173,7 +189,23 @@ def run_block_cases():
     return out
 
 
+def main_periodic():
+    import json
+    cases = {}
+    for case in PERIODIC_CASES:
+        res = run_calc_case(case)
+        for k, v in res.items():
+            cases[f"{case['name']}/{k}"] = v
+        print(case["name"], "periodic =", case["periodic"], "V[0] =", res["V"][0])
+    np.savez_compressed(os.path.join(HERE, "periodic_cases.npz"), **cases)
+    with open(os.path.join(HERE, "periodic_cases.json"), "w") as f:
+        json.dump(PERIODIC_CASES, f, indent=1)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "periodic":   # only the 2-D periodic fixtures
+        return main_periodic()
+    main_periodic()
     cases = {}
     for case in CALC_CASES:
         res = run_calc_case(case)

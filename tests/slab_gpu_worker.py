@@ -26,9 +26,18 @@ def main():
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    # TPME_SLAB_ONE_GPU=1: every rank is its own process on cuda:0 (a one-GPU box still runs the real
+    # multi-process path: CUDA IPC peer mappings, the flag barrier, the fused push kernels and the peer
+    # all-reduce; NCCL refuses two ranks on one device, so torch.distributed runs over gloo there)
+    one_gpu = os.environ.get("TPME_SLAB_ONE_GPU") == "1"
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if one_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=dev)
 
     pos64, q64, cell64, idx_cpu, d64 = rocksalt(8, dtype=torch.float64, cutoff=5.0)
     q64 = torch.cat([q64, 0.5 * q64 + 0.25], dim=1)
@@ -40,7 +49,7 @@ def main():
         refs[method] = oracle.calculator_step(spec, q64.numpy(), cell64.numpy(), pos64.numpy(), idx_cpu.numpy(),
                                               d64.numpy(), mesh_spacing, 4, method, grad_out=gout64.numpy())
 
-    for transport in ("nccl", "p2p", "p2p-copy"):
+    for transport in (("p2p", "p2p-copy") if one_gpu else ("nccl", "p2p", "p2p-copy")):
         for dtype in (torch.float64, torch.float32):
             for method in ("P3M", "Lagrange"):
                 if method == "P3M":
@@ -56,8 +65,7 @@ def main():
                     p.grad = q.grad = d.grad = None
                     V = calc(q, cell64.to(dev, dtype), p, idx_cpu.to(dev), d)
                     (V * gout64.to(dev, dtype)).sum().backward()
-                dd = d.grad.clone()
-                dist.all_reduce(dd)
+                dd = d.grad.clone()   # replicated pair list (shard_pairs=True): the full gradient on every rank
                 ref = refs[method]
                 if transport.startswith("p2p"):
                     calc._slab_cfg.filter.exchange.check()
@@ -66,7 +74,7 @@ def main():
                     return float(np.abs(a.detach().cpu().double().numpy() - b).max() / max(np.abs(b).max(), 1e-300))
 
                 errs = torch.tensor([err(V, ref["V"]), err(p.grad, ref["dpos"]), err(q.grad, ref["dq"]),
-                                     err(dd, ref["dd"])], device=dev, dtype=torch.float64)
+                                     err(dd, ref["dd"])], device="cpu" if one_gpu else dev, dtype=torch.float64)
                 dist.all_reduce(errs, op=dist.ReduceOp.MAX)
                 if rank == 0:
                     print(json.dumps(dict(transport=transport, dtype=str(dtype).replace("torch.", ""), method=method,

@@ -54,15 +54,21 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc != 0 and b"dtype" in lib.tpme_last_error()
 
 
-def test_cpu_tensors_fail_loudly():
-    """There is no CPU fallback: CPU tensors raise instead of silently computing elsewhere."""
+def test_kernel_bindings_refuse_cpu_tensors():
+    """
+    Device dispatch happens in the Python classes (CPU tensors -> torchpme_b200._cpu, the torch
+    formulation); the kernel bindings themselves never compute anything for a CPU tensor and never
+    fall back: they raise.
+    """
     import torch
 
-    import torchpme_b200 as tp
+    from torchpme_b200 import _native
 
-    calc = tp.PMECalculator(tp.CoulombPotential(smearing=0.5), mesh_spacing=0.25)
-    with pytest.raises(tp.NativeLibraryError, match="CUDA-only"):
-        calc(torch.ones(2, 1), torch.eye(3), torch.rand(2, 3), torch.tensor([[0, 1]]), torch.tensor([0.5]))
+    with pytest.raises(_native.NativeLibraryError, match="CUDA-only"):
+        _native.spread(torch.rand(2, 3), torch.ones(2, 1), [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0], (8, 8, 8), 4, 0)
+    with pytest.raises(_native.NativeLibraryError, match="CUDA-only"):
+        _native.pair_forward(torch.ones(2, 1), torch.tensor([[0, 1]]), torch.tensor([0.5]), None, None, False,
+                             _native.make_pair_potential(1, 0.5))
 
 
 def test_slab_and_peer_entry_points_validate_arguments_without_a_gpu():

@@ -1,0 +1,131 @@
+"""
+CPU tensors (device dispatch to torchpme_b200._cpu, the package's own torch formulation) against the
+golden tensors of the unmodified reference: BASELINE config c1 (CsCl, PMECalculator, fp64, CPU) and
+every other calculator golden incl. the 2-D periodic ones, values and all gradients; the reference's
+workflow expectations (dtype / device preserved, `examples/basic-usage.py` numbers); the inspection
+attributes of MeshInterpolator (lib/mesh_interpolator.py:65-79); double backward.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, b200_potential, case_arrays, load_calculator_cases
+
+CASES, DATA = load_calculator_cases()
+with open(os.path.join(GOLDEN, "periodic_cases.json")) as f:
+    P_CASES = json.load(f)
+P_DATA = np.load(os.path.join(GOLDEN, "periodic_cases.npz"))
+ALL = [(c, DATA) for c in CASES] + [(c, P_DATA) for c in P_CASES]
+
+
+def _norm(ref, natural):
+    m = float(np.abs(ref).max())
+    return m if m > 1e-6 * natural else natural
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("case, data", ALL, ids=[c["name"] for c, _ in ALL])
+def test_cpu_calculators_match_reference_golden(case, data, dtype):
+    import torchpme_b200 as tp
+
+    g = case_arrays(data, case["name"])
+    q = torch.tensor(g["charges"], dtype=dtype, requires_grad=True)
+    cell = torch.tensor(g["cell"], dtype=dtype, requires_grad=True)
+    pos = torch.tensor(g["positions"], dtype=dtype, requires_grad=True)
+    d = torch.tensor(g["neighbor_distances"], dtype=dtype, requires_grad=True)
+    idx = torch.tensor(g["neighbor_indices"])
+    cls = tp.PMECalculator if case["calc"] == "pme" else tp.P3MCalculator
+    calc = cls(b200_potential(tp, case["pot"], dtype=dtype), mesh_spacing=case["mesh_spacing"],
+               interpolation_nodes=case["nodes"], full_neighbor_list=case["full"])
+    periodic = torch.tensor(case["periodic"]) if "periodic" in case else None
+    V = calc.forward(q, cell, pos, idx, d, periodic=periodic)
+    assert V.dtype == dtype and V.device.type == "cpu"          # tests/calculators/test_workflow.py:112-123
+    (V * torch.tensor(g["grad_out"], dtype=dtype)).sum().backward()
+    tol = 1e-9 if dtype == torch.float64 else 1e-3
+    scale = float(np.abs(g["V"]).max())
+    assert np.abs(V.detach().numpy() - g["V"]).max() / scale < tol
+    for name, t in (("dq", q), ("dd", d), ("dpos", pos), ("dcell", cell)):
+        # fp32 forces of the perfect CsCl crystal are rounding noise around zero in the reference too
+        if dtype == torch.float32 and case.get("system") == "cscl" and name == "dpos":
+            continue
+        assert np.abs(t.grad.numpy() - g[name]).max() / _norm(g[name], scale) < tol, name
+
+
+def test_c1_cscl_madelung_on_cpu():
+    """BASELINE config c1 / examples/basic-usage.py: CsCl, PMECalculator, fp64, CPU -> Madelung constant"""
+    import torchpme_b200 as tp
+
+    pos = torch.tensor([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]], dtype=torch.float64)
+    q = torch.tensor([[1.0], [-1.0]], dtype=torch.float64)
+    cell = torch.eye(3, dtype=torch.float64)
+    from oracle import pme_oracle as oracle   # test utility: the neighbor list only
+    idx, d, _ = oracle.neighbor_list(pos.numpy(), cell.numpy(), 1.0)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=0.2), mesh_spacing=0.05).to(torch.float64)
+    V = calc(q, cell, pos, torch.tensor(idx), torch.tensor(d))
+    madelung = -float((V * q).sum())          # unit cell edge 1: tests/helpers.py:34 (2.0353610945), rtol of the reference's test
+    assert abs(madelung - 2.0353610945) < 9e-4 * 2.0353610945, madelung
+
+
+def test_mesh_interpolator_inspection_attributes():
+    """interpolation_weights, x/y/z_indices, x/y/z_shifts as the reference exposes them"""
+    import torchpme_b200 as tp
+
+    rng = np.random.default_rng(0)
+    cell = torch.tensor(np.eye(3) * 5.0 + rng.uniform(-0.3, 0.3, (3, 3)))
+    pos = torch.tensor(rng.uniform(-2, 7, (11, 3)))
+    ns = torch.tensor([6, 7, 8])
+    for method, nodes in (("P3M", 3), ("Lagrange", 4), ("P3M", 5)):
+        mi = tp.lib.MeshInterpolator(cell, ns, nodes, method)
+        mi.compute_weights(pos)
+        w = mi.interpolation_weights
+        assert w.shape == (nodes, 11, 3)
+        assert torch.allclose(w.sum(0), torch.ones(11, 3, dtype=torch.float64), atol=1e-12)   # partition of unity
+        for name, n_axis in (("x", 6), ("y", 7), ("z", 8)):
+            ind, sh = getattr(mi, f"{name}_indices"), getattr(mi, f"{name}_shifts")
+            assert ind.shape == (nodes ** 3, 11) and sh.shape == (nodes ** 3,)
+            assert int(ind.min()) >= 0 and int(ind.max()) < n_axis
+        # the attributes reproduce points_to_mesh exactly (mesh_interpolator.py:411-426)
+        weights = torch.tensor(rng.normal(size=(11, 1)))
+        rho = mi.points_to_mesh(weights)
+        xs, ys, zs = mi.x_shifts, mi.y_shifts, mi.z_shifts
+        ref = torch.zeros(1, 6, 7, 8, dtype=torch.float64)
+        contrib = weights[:, 0] * w[xs, :, 0] * w[ys, :, 1] * w[zs, :, 2]
+        ref[0].index_put_((mi.x_indices, mi.y_indices, mi.z_indices), contrib, accumulate=True)
+        assert torch.allclose(rho, ref, atol=1e-13)
+    try:
+        from _reference_import import available, import_reference
+    except ImportError:
+        return
+    if available():
+        ref = import_reference()
+        rmi = ref.lib.MeshInterpolator(cell, ns, 4, "Lagrange")
+        rmi.compute_weights(pos)
+        mi = tp.lib.MeshInterpolator(cell, ns, 4, "Lagrange")
+        mi.compute_weights(pos)
+        assert torch.allclose(mi.interpolation_weights, rmi.interpolation_weights, atol=1e-13)
+        for name in ("x_indices", "y_indices", "z_indices", "x_shifts", "y_shifts", "z_shifts"):
+            assert torch.equal(getattr(mi, name), getattr(rmi, name)), name
+
+
+def test_double_backward_on_cpu():
+    """force matching needs create_graph=True through the calculator (the reference supports it)"""
+    import torchpme_b200 as tp
+
+    g = case_arrays(DATA, "rand_p3m_n4_coulomb")
+    dt = torch.float64
+    q = torch.tensor(g["charges"], dtype=dt)
+    cell = torch.tensor(g["cell"], dtype=dt)
+    pos = torch.tensor(g["positions"], dtype=dt, requires_grad=True)
+    idx = torch.tensor(g["neighbor_indices"])
+    pot = tp.CoulombPotential(smearing=0.9, prefactor=1.7).to(dt)
+    pot.smearing.requires_grad_(True)        # a potential parameter as a leaf
+    calc = tp.P3MCalculator(pot, mesh_spacing=0.8, full_neighbor_list=False)
+    d = torch.tensor(g["neighbor_distances"], dtype=dt)
+    V = calc(q, cell, pos, idx, d)
+    (forces,) = torch.autograd.grad((V * q).sum(), pos, create_graph=True)
+    loss = (forces ** 2).sum()
+    (g_smearing,) = torch.autograd.grad(loss, pot.smearing)
+    assert torch.isfinite(g_smearing) and float(g_smearing.abs()) > 0

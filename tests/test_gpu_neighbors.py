@@ -1,0 +1,113 @@
+"""
+Neighbor list built on the GPU (torchpme_b200.neighbors: cell-list kernels tpme_neighbor_count /
+tpme_neighbor_fill) against the brute-force oracle (oracle.neighbor_list, the stand-in for the
+reference's external `vesin` dependency, tests/helpers.py:240-275): the SAME set of (i, j, image)
+pairs with the same distances, for cubic / triclinic / smaller-than-cutoff cells, half and full lists,
+fp32 and fp64, 2-D periodic and open systems; at 1 M atoms against the pair list of the synthetic
+generator; and the differentiable distances against autograd through the reference formula.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, rocksalt
+from oracle import pme_oracle as oracle
+from test_neighbors import CELLS, _canonical
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("full", [False, True], ids=["half", "full"])
+@pytest.mark.parametrize("cell_name", sorted(CELLS))
+def test_pair_set_matches_oracle(cell_name, full, dtype):
+    from torchpme_b200.neighbors import neighbor_list
+
+    cell = CELLS[cell_name]
+    rng = np.random.default_rng(11)
+    n = 60 if "small" in cell_name else 400
+    pos = rng.uniform(-0.3, 1.3, (n, 3)) @ cell        # some atoms outside the cell
+    cutoff = 3.0
+    idx, d, s = neighbor_list(torch.tensor(pos, dtype=dtype, device="cuda"), torch.tensor(cell, dtype=dtype, device="cuda"),
+                              cutoff, full_neighbor_list=full)
+    o_idx, o_d, o_s = oracle.neighbor_list(pos, cell, cutoff, full=full)
+    # pairs closer to the cutoff than the working precision resolves may legitimately differ
+    eps = 1e-9 if dtype == torch.float64 else 2e-5
+    sure = np.abs(o_d - cutoff) > eps
+    d_np = d.double().cpu().numpy()
+    sure_gpu = np.abs(d_np - cutoff) > eps
+    if full:
+        got = np.concatenate([idx.cpu().numpy(), s.cpu().numpy()], axis=1)[sure_gpu]
+        want = np.concatenate([o_idx, o_s], axis=1)[sure]
+        got = got[np.lexsort(got.T[::-1])]
+        want = want[np.lexsort(want.T[::-1])]
+        assert got.shape == want.shape and np.array_equal(got, want)
+    else:
+        rows, dist = _canonical(idx.cpu().numpy()[sure_gpu], d_np[sure_gpu], s.cpu().numpy()[sure_gpu])
+        o_rows, o_dist = _canonical(o_idx[sure], o_d[sure], o_s[sure])
+        assert rows.shape == o_rows.shape and np.array_equal(rows, o_rows)
+        assert np.abs(dist - o_dist).max() < (1e-12 if dtype == torch.float64 else 1e-5)
+
+
+@pytest.mark.parametrize("periodic", [(True, True, False), (False, False, False)])
+def test_partially_periodic(periodic):
+    """slab / open boundaries: images only along the periodic axes (checked against a brute force)"""
+    from torchpme_b200.neighbors import neighbor_list
+
+    cell = np.eye(3) * 9.0
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(0, 1, (300, 3)) @ cell
+    cutoff = 2.5
+    idx, d, s = neighbor_list(torch.tensor(pos, device="cuda"), torch.tensor(cell, device="cuda"), cutoff,
+                              periodic=periodic)
+    o_idx, o_d, o_s = oracle.neighbor_list(pos, cell, cutoff)
+    ok = np.ones(len(o_d), dtype=bool)
+    for a in range(3):
+        if not periodic[a]:
+            ok &= o_s[:, a] == 0
+    rows, dist = _canonical(idx.cpu().numpy(), d.cpu().numpy(), s.cpu().numpy())
+    o_rows, o_dist = _canonical(o_idx[ok], o_d[ok], o_s[ok])
+    assert np.array_equal(rows, o_rows) and np.abs(dist - o_dist).max() < 1e-12
+
+
+def test_distances_are_differentiable_like_the_reference_formula():
+    """distances_from(positions, cell, idx, shifts): gradients to positions AND cell (the path MD codes use)"""
+    from torchpme_b200.neighbors import distances_from, neighbor_list
+
+    pos, q, cell, _, _ = rocksalt(5, dtype=torch.float64, device="cuda", cutoff=5.0)
+    cell = cell + 0.3 * torch.rand(3, 3, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    idx, d, s = neighbor_list(pos, cell, 4.0)
+    p = pos.clone().requires_grad_(True)
+    c = cell.clone().requires_grad_(True)
+    dd = distances_from(p, c, idx, s)
+    assert rel_err(dd.detach(), d) < 1e-12
+    w = torch.randn(dd.shape, dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    (dd * w).sum().backward()
+    # analytic: d|r_ij|/dr_j = r_ij / |r_ij|, d/dcell = S^T (r_ij / |r_ij|)
+    rij = (pos[idx[:, 1]] - pos[idx[:, 0]] + s.double() @ cell)
+    unit = rij / rij.norm(dim=1, keepdim=True) * w[:, None]
+    gp = torch.zeros_like(pos).index_add_(0, idx[:, 1], unit).index_add_(0, idx[:, 0], -unit)
+    gc = s.double().T @ unit
+    assert rel_err(p.grad, gp) < 1e-12 and rel_err(c.grad, gc) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_one_million_atoms_against_the_generator(dtype):
+    """c4-size system: same number of pairs and the same distance multiset as the lattice-topology list"""
+    from torchpme_b200.neighbors import neighbor_list
+
+    pos, q, cell, idx_ref, d_ref = rocksalt(100, dtype=torch.float64, device="cuda", cutoff=6.0)
+    idx, d, s = neighbor_list(pos.to(dtype), cell.to(dtype), 6.0)
+    eps = 1e-9 if dtype == torch.float64 else 5e-5
+    sure = (d.double() - 6.0).abs() > eps
+    sure_ref = (d_ref - 6.0).abs() > eps
+    assert int(sure.sum()) == int(sure_ref.sum())
+    assert idx.shape[0] > 16_000_000
+    a = torch.sort(d.double()[sure]).values
+    b = torch.sort(d_ref[sure_ref]).values
+    assert float((a - b).abs().max()) < (1e-10 if dtype == torch.float64 else 2e-5)
+    # every unordered pair once: degree sums agree atom by atom
+    deg = torch.zeros(pos.shape[0], device="cuda").index_add_(0, idx[sure].reshape(-1), torch.ones(2 * int(sure.sum()), device="cuda"))
+    deg_ref = torch.zeros(pos.shape[0], device="cuda").index_add_(0, idx_ref[sure_ref].reshape(-1),
+                                                                  torch.ones(2 * int(sure_ref.sum()), device="cuda"))
+    assert torch.equal(deg, deg_ref)

@@ -190,3 +190,25 @@ def test_two_gpus_against_oracle():
         tol = 1e-9 if res["dtype"] == "float64" else 1e-3
         for key in ("V", "dpos", "dq", "dd"):
             assert res[key] < tol, res
+
+
+def test_two_ranks_on_one_gpu_against_oracle():
+    """
+    The real multi-process slab path on a ONE-GPU box: two processes share cuda:0 (torch.distributed
+    over gloo, TPME_SLAB_ONE_GPU=1), so CUDA IPC mappings, the device-side flag barrier, the FFT kernels
+    that store into the peer's arrays and the peer all-reduce all run between two processes, against
+    the numpy oracle.  The GPU time-slices the two contexts, so the barriers take milliseconds.
+    """
+    world = 2
+    env = dict(os.environ, TPME_SLAB_ONE_GPU="1", TPME_PEER_TIMEOUT="120")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(HERE, "slab_gpu_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    lines = [json.loads(line) for line in out.stdout.splitlines() if line.startswith("{")]
+    assert len(lines) == 8     # 2 transports x 2 dtypes x 2 methods
+    for res in lines:
+        tol = 1e-9 if res["dtype"] == "float64" else 1e-3
+        for key in ("V", "dpos", "dq", "dd"):
+            assert res[key] < tol, res

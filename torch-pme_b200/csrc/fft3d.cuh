@@ -21,6 +21,7 @@
 //   * G(k) is evaluated from per-CTA axis tables (k = a[ix] + b[iy,iz], sines by angle addition),
 //     one exp and one division per k-point.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "green.cuh"
@@ -582,8 +583,13 @@ rows_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int64_t n_row
 // plane [NY][NZ/2+1] in shared memory, so the z and y passes cost one global read and one global
 // write in total (used when the plane fits: <= 128 x 128 here).
 // ---------------------------------------------------------------------------------------
+// the plane kernels hold at most one radix-16 group of complex values per thread (<= 92 registers in
+// fp64): up to 512 threads per CTA, so that the single CTA an SM holds (the plane fills its shared
+// memory) has enough warps to hide the global and shared-memory latency
+constexpr int kPlaneMaxThreads = 512;
+
 template <typename T, int NY, int NZ>
-__global__ void __launch_bounds__(MaxThreads<T>::value)
+__global__ void __launch_bounds__(kPlaneMaxThreads)
 plane_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int rows_per_chunk) {
   constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1;
   using CZ = Chain<H>;
@@ -691,7 +697,7 @@ plane_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int rows_per
 }
 
 template <typename T, int NY, int NZ>
-__global__ void __launch_bounds__(MaxThreads<T>::value)
+__global__ void __launch_bounds__(kPlaneMaxThreads)
 plane_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int rows_per_chunk) {
   constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1;
   using CZ = Chain<H>;
@@ -901,13 +907,22 @@ int dispatch_lines(int n, void* data, int n_outer, int n_inner, int64_t ls, int 
 template <typename T, int NY, int NZ>
 int launch_plane(bool forward, const void* in, void* out, int n_planes, cudaStream_t s) {
   constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1;
-  constexpr int threads = MaxThreads<T>::value;
   constexpr int items_per_row = H / Chain<H>::RA > 0 ? H / Chain<H>::RA : 1;
+  // threads: one radix item of the y pass each, up to the launch bound (TPME_PLANE_THREADS overrides)
+  static const int env_threads = [] { const char* e = getenv("TPME_PLANE_THREADS"); return e ? atoi(e) : 0; }();
+  int threads = (P * (NY / Chain<NY>::RA) + 31) / 32 * 32;
+  if (threads > kPlaneMaxThreads) threads = kPlaneMaxThreads;
+  if (env_threads >= 32 && env_threads <= kPlaneMaxThreads) threads = env_threads / 32 * 32;
+  if (threads < 64) threads = 64;
   int rows = threads / items_per_row;
   if (rows < 1) rows = 1;
   if (rows > NY) rows = NY;
-  const size_t smem = ((size_t)NY * P + (Chain<H>::NG == 2 ? (size_t)rows * P1 : 0) + NZ / 2 + NY / 2) * sizeof(C2<T>);
-  if (smem > 200 * 1024) return -1;
+  auto smem_of = [&](int r) {
+    return ((size_t)NY * P + (Chain<H>::NG == 2 ? (size_t)r * P1 : 0) + NZ / 2 + NY / 2) * sizeof(C2<T>);
+  };
+  while (rows > 1 && smem_of(rows) > 216 * 1024) rows >>= 1;   // the exchange buffer of the z pass shrinks first
+  const size_t smem = smem_of(rows);
+  if (smem > 216 * 1024) return -1;
   if (forward) {
     if (int rc = allow_smem(plane_r2c_kernel<T, NY, NZ>, smem)) return rc;
     plane_r2c_kernel<T, NY, NZ><<<n_planes, threads, smem, s>>>((const T*)in, (C2<T>*)out, rows);

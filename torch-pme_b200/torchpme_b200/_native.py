@@ -81,6 +81,12 @@ class _NeighborSearch(ctypes.Structure):
     ]
 
 
+class _TilePlan(ctypes.Structure):
+    _fields_ = [(name, ctypes.c_int) for name in (
+        "nx", "ny", "nz", "nodes", "tx", "ty", "zw", "npx", "npy", "nzc", "n_bins", "row_stride",
+        "plane_stride", "smem_bytes", "spread_threads", "gather_threads", "spread_batch")]
+
+
 class _SlabPeers(ctypes.Structure):
     _fields_ = [
         ("n_ranks", ctypes.c_int),
@@ -108,6 +114,11 @@ SIGNATURES = {
     "tpme_gather_vjp_slab": ([_i, _vp, _vp, _vp, _i64, _i, _dp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp,
                               _i, _vp, ctypes.POINTER(_PointEpilogue), _vp], _i),
     "tpme_slab_select_points": ([_i, _vp, _i64, _dp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
+    "tpme_tile_plan_make": ([_i, _i, _i, _i, _i, _i, _i64, ctypes.POINTER(_TilePlan)], _i),
+    "tpme_tile_sort": ([_i, ctypes.POINTER(_TilePlan), _vp, _i64, _dp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "tpme_tile_spread": ([_i, ctypes.POINTER(_TilePlan), _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp], _i),
+    "tpme_tile_gather": ([_i, ctypes.POINTER(_TilePlan), _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _dp, _i, _vp, _vp,
+                          _vp, _i, _vp, ctypes.POINTER(_PointEpilogue), _vp], _i),
     "tpme_slab_fft_yz": ([_i, _i, _vp, _vp, _i, _i, _i, _vp], _i),
     "tpme_slab_fft_x_green": ([_i, _vp, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
     "tpme_slab_exchange_copy": ([_i, _vp, ctypes.POINTER(_vp), _i, _i, _i, _i64, _i64, _i64, _i64, _i64,
@@ -247,11 +258,114 @@ def slab_select_points(positions, r2u, ns, nodes: int, slab):
     return lst, count
 
 
-def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=None, point_list=None):
+# --------------------------------------------------------------------------------------
+# tiled mesh interpolation (cell-sorted atoms, shared-memory pencils, TMA bulk copies)
+# --------------------------------------------------------------------------------------
+#: "auto": use the tiled kernels whenever the mesh / stencil is covered and the system is large
+#: enough to pay for the sort; "off": always the direct kernels; "on": tiled whenever covered
+TILE_MODE = os.environ.get("TPME_TILES", "auto")
+TILE_MIN_POINTS = int(os.environ.get("TPME_TILE_MIN_POINTS", "4096"))
+
+
+class TileSort:
+    """
+    The points of one spread / gather sequence binned by mesh tile (`tpme_tile_sort`): per-point
+    records in bin order, the permutation and the bin starts.  Built once per set of positions and
+    shared by the forward and backward launches of a step.
+    """
+
+    __slots__ = ("plan", "bin_start", "rec", "idx", "n_points", "r2u", "dtype", "positions")
+
+    def __init__(self, plan, positions, r2u):
+        lib = load()
+        n = positions.shape[0]
+        dev = positions.device
+        self.plan, self.n_points, self.r2u, self.dtype = plan, n, r2u, positions.dtype
+        self.positions = positions
+        counts = torch.empty(plan.n_bins, dtype=torch.int32, device=dev)
+        self.bin_start = torch.empty(plan.n_bins + 1, dtype=torch.int32, device=dev)
+        key_rank = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
+        self.rec = torch.empty((max(n, 1), 4), dtype=positions.dtype, device=dev)
+        self.idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        with _on(positions, "positions"):
+            _check(lib.tpme_tile_sort(_dtype_id(positions), ctypes.byref(plan), _dev(positions, "positions"), n,
+                                      _mat9(r2u), _dev(counts, "bin_count"),
+                                      _dev(self.bin_start, "bin_start"), _dev(key_rank, "key_rank"),
+                                      _dev(self.rec, "sorted_rec"), _dev(self.idx, "sorted_idx"), _stream()),
+                   "tpme_tile_sort")
+        _count(3)
+
+
+_tile_plans: dict = {}
+
+
+def tile_plan(dtype, ns, nodes: int, method: int, n_points: int):
+    """tiling of the mesh for the tiled kernels, or None when they do not cover this case"""
+    if TILE_MODE == "off" or n_points <= 0 or (TILE_MODE != "on" and n_points < TILE_MIN_POINTS):
+        return None
+    # the plan depends on the point count only through the block sizes: bucket it
+    key = (dtype, tuple(int(v) for v in ns), int(nodes), int(method), int(n_points).bit_length())
+    if key in _tile_plans:
+        return _tile_plans[key]
+    lib = load()
+    plan = _TilePlan()
+    rc = lib.tpme_tile_plan_make(0 if dtype == torch.float32 else 1, int(ns[0]), int(ns[1]), int(ns[2]),
+                                 int(nodes), int(method), int(n_points), ctypes.byref(plan))
+    if rc not in (0, 3):
+        _check(rc, "tpme_tile_plan_make")
+    _tile_plans[key] = plan if rc == 0 else None
+    return _tile_plans[key]
+
+
+def tile_sort(positions, r2u, ns, nodes: int, method: int):
+    """TileSort of `positions`, or None when the direct kernels should be used"""
+    if not positions.is_cuda or positions.dtype not in (torch.float32, torch.float64):
+        return None
+    plan = tile_plan(positions.dtype, ns, nodes, method, positions.shape[0])
+    return TileSort(plan, positions, r2u) if plan is not None else None
+
+
+def tile_spread(tiles: TileSort, weights, method: int, out=None):
+    lib = load()
+    n, c = weights.shape
+    plan = tiles.plan
+    if out is None:
+        out = torch.empty((c, plan.nx, plan.ny, plan.nz), dtype=weights.dtype, device=weights.device)
+    with _on(weights, "particle_weights"):
+        _check(lib.tpme_tile_spread(_dtype_id(weights), ctypes.byref(plan), _dev(tiles.rec, "sorted_rec"),
+                                    _dev(tiles.idx, "sorted_idx"), _dev(tiles.bin_start, "bin_start"),
+                                    _dev(weights, "particle_weights"), n, c, method, _dev(out, "mesh"), 0,
+                                    _stream()), "tpme_tile_spread")
+    _count()
+    return out
+
+
+def tile_gather(tiles: TileSort, mesh, method: int, values=None, dvalues=None, grad_positions=None,
+                coef=None, accumulate=False, grad_r2u=None, epilogue=None):
+    lib = load()
+    c = mesh.shape[0]
+    with _on(mesh, "mesh"):
+        _check(lib.tpme_tile_gather(_dtype_id(mesh), ctypes.byref(tiles.plan), _dev(mesh, "mesh"),
+                                    _dev(tiles.rec, "sorted_rec"), _dev(tiles.idx, "sorted_idx"),
+                                    _dev(tiles.bin_start, "bin_start"), _dev(tiles.positions, "positions"),
+                                    _dev(coef, "coef"), tiles.n_points, c, _mat9(tiles.r2u), method,
+                                    _dev(values, "values"), _dev(dvalues, "dvalues"),
+                                    _dev(grad_positions, "grad_positions"), int(accumulate),
+                                    _dev(grad_r2u, "grad_r2u"),
+                                    ctypes.byref(epilogue) if epilogue is not None else None, _stream()),
+               "tpme_tile_gather")
+    _count()
+
+
+def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=None, point_list=None,
+           tiles: TileSort | None = None):
     """
     `slab` = (x0, nx_local): spread into the local x slab (C, nx_local, ny, nz) only;
-    `point_list` = result of :func:`slab_select_points` for that slab
+    `point_list` = result of :func:`slab_select_points` for that slab;
+    `tiles` = :class:`TileSort` of `positions`: use the tiled kernel
     """
+    if tiles is not None and slab is None:
+        return tile_spread(tiles, weights, method, out=out)
     lib = load()
     n, c = weights.shape
     nx, ny, nz = ns
@@ -290,7 +404,8 @@ def _slab_of(mesh, slab):
 
 
 def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want_grad=False,
-           values_out=None, epilogue: _PointEpilogue | None = None, slab=None, point_list=None):
+           values_out=None, epilogue: _PointEpilogue | None = None, slab=None, point_list=None,
+           tiles: TileSort | None = None):
     """
     plain gather, or (with `epilogue` and `values_out`) the fused accumulate form.
     `slab` = (x0, nx_global): `mesh` is the local x slab and the results are partial sums.
@@ -302,6 +417,9 @@ def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want
     if values is None and want_values:
         values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device)
     dvalues = torch.empty((n, c, 3), dtype=mesh.dtype, device=mesh.device) if want_grad else None
+    if tiles is not None and slab is None and n > 0:
+        tile_gather(tiles, mesh, method, values=values, dvalues=dvalues, epilogue=epilogue)
+        return values, dvalues
     with _on(mesh, "mesh"):
         _check(lib.tpme_gather_slab(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"), n,
                                     c, _mat9(r2u), nx, ny, nz, x0, nxl, *_list_args(point_list), nodes, method,
@@ -314,7 +432,8 @@ def gather(mesh, positions, r2u, nodes: int, method: int, want_values=True, want
 
 def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positions=None,
                want_values=False, want_grad_r2u=False, values_out=None,
-               epilogue: _PointEpilogue | None = None, slab=None, point_list=None):
+               epilogue: _PointEpilogue | None = None, slab=None, point_list=None,
+               tiles: TileSort | None = None):
     """returns (grad_positions, values | None, grad_r2u (3,3) | None); `slab` as in :func:`gather`"""
     lib = load()
     c, nx, ny, nz, x0, nxl = _slab_of(mesh, slab)
@@ -326,6 +445,10 @@ def gather_vjp(mesh, positions, coef, r2u, nodes: int, method: int, grad_positio
     if values is None and want_values:
         values = torch.empty((n, c), dtype=mesh.dtype, device=mesh.device)
     grad_r2u = torch.zeros((3, 3), dtype=mesh.dtype, device=mesh.device) if want_grad_r2u else None
+    if tiles is not None and slab is None and n > 0 and c > 0:
+        tile_gather(tiles, mesh, method, values=values, grad_positions=grad_positions, coef=coef,
+                    accumulate=accumulate, grad_r2u=grad_r2u, epilogue=epilogue)
+        return grad_positions, values, grad_r2u
     with _on(mesh, "mesh"):
         _check(lib.tpme_gather_vjp_slab(_dtype_id(mesh), _dev(mesh, "mesh"), _dev(positions, "positions"),
                                         _dev(coef, "coef"), n, c, _mat9(r2u), nx, ny, nz, x0, nxl,
@@ -588,7 +711,7 @@ class PeerBuffer:
             pass
 
 
-def peer_barrier(flag_ptrs, rank: int, epoch, error_flag, timeout_seconds: float = 5.0):
+def peer_barrier(flag_ptrs, rank: int, epoch, error_flag, timeout_seconds: float = 60.0):
     lib = load()
     n = len(flag_ptrs)
     arr = (_vp * n)(*[int(p) for p in flag_ptrs])

@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 from torch.autograd.function import once_differentiable
 
-from . import _native
+from . import _cpu, _native
 from ._checks import validate_parameters
 from .mesh import KSpaceFilter, MeshInterpolator, P3MKSpaceFilter, geometry_of
 from .potentials import Potential
@@ -86,20 +86,23 @@ class _FusedMeshPotential(torch.autograd.Function):
         # the pair sum is independent of the mesh pipeline until the gather epilogue: run it (and
         # the zero fill of its accumulator) on a side stream -- a parallel branch when the step is
         # captured in a CUDA graph.  `out` is next touched on the main stream after the join.
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(q.device)
         side = _side_stream(q.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             out.zero_()
             _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
-        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+        # atoms binned by mesh tile once per step: the spread, the gather and both backward launches
+        # stage their pencil of the mesh in shared memory (csrc/tiles.cu); None = direct kernels
+        tiles = _native.tile_sort(pos, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
         green = _native.make_green(scale=1.0, **cfg.green_args)
         phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
         main.wait_stream(side)
         epi = _native.make_epilogue(q, dc, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume)
         _, dvalues = _native.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=need_pos,
-                                    values_out=out, epilogue=epi)
-        ctx.cfg = cfg
+                                    values_out=out, epilogue=epi, tiles=tiles)
+        ctx.cfg, ctx.tiles = cfg, tiles
         ctx.save_for_backward(q, pos, d, idx, mask_u8, dvalues)
         return out
 
@@ -107,12 +110,12 @@ class _FusedMeshPotential(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, grad_out):
         q, pos, d, idx, mask_u8, dvalues = ctx.saved_tensors
-        cfg = ctx.cfg
+        cfg, tiles = ctx.cfg, ctx.tiles
         need_q, need_pos, need_d = ctx.needs_input_grad[:3]
         g = grad_out.contiguous()
         g_q = torch.zeros_like(q) if need_q else None
         g_d = None
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(q.device)
         side = _side_stream(q.device)
         forked = False
         if need_q or need_d:
@@ -127,7 +130,7 @@ class _FusedMeshPotential(torch.autograd.Function):
                                       grad_pairs_out=g_d)
         g_pos = None
         if need_q or need_pos:
-            rho_g = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+            rho_g = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
             green = _native.make_green(scale=1.0, **cfg.green_args)
             psi, _, dc_g = _native.kfilter_apply(rho_g, green, want_dc=True)
             if forked and need_q:
@@ -138,9 +141,10 @@ class _FusedMeshPotential(torch.autograd.Function):
                                         vjp_scale=cfg.half_ivolume)
             if need_pos:
                 g_pos, _, _ = _native.gather_vjp(psi, pos, q, cfg.r2u, cfg.nodes, cfg.method,
-                                                 values_out=g_q, epilogue=epi)
+                                                 values_out=g_q, epilogue=epi, tiles=tiles)
             else:
-                _native.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi)
+                _native.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi,
+                               tiles=tiles)
         if forked:
             main.wait_stream(side)
         return g_q, g_pos, g_d, None, None, None
@@ -163,6 +167,12 @@ class Calculator(torch.nn.Module):
         pot = self.potential
         mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
         descriptor = pot._native_descriptor()
+        # the in-kernel potentials take smearing / prefactor by value: when any of them needs a
+        # gradient the per-pair values come from the potential's own differentiable torch code
+        # (reference: potentials/potential.py:106-138 feeds autograd the same way)
+        if descriptor is not None and (not charges.is_cuda or any(
+                t.requires_grad for t in list(pot.parameters()) + list(pot.buffers()))):
+            descriptor = None
         if descriptor is not None and pot.smearing is not None:
             kind, exponent = descriptor
             smearing, prefactor = pot._scalars()
@@ -177,6 +187,8 @@ class Calculator(torch.nn.Module):
                 bare = bare * (1 - pot.f_cutoff(neighbor_distances, pair_mask))
         else:
             bare = pot.sr_from_dist(neighbor_distances, pair_mask)
+        if not charges.is_cuda:               # device dispatch: CPU tensors use the torch formulation
+            return _cpu.pair_sum(charges, neighbor_indices, bare.to(charges.dtype), self.full_neighbor_list)
         native_pot = _native.make_pair_potential(0)
         return _PairSum.apply(charges, bare.to(charges.dtype), neighbor_indices, mask_u8,
                               native_pot, self.full_neighbor_list)
@@ -232,16 +244,13 @@ class PMECalculator(Calculator):
 
     def forward(self, charges, cell, positions, neighbor_indices, neighbor_distances,
                 periodic=None, node_mask=None, pair_mask=None, kvectors=None):
-        if not self._fast_path_ok(cell, periodic, node_mask, kvectors):
+        # the fused node is CUDA only; CPU tensors go through the modular blocks, which dispatch to the
+        # torch formulation of _cpu.py (CUDA tensors never do)
+        if not positions.is_cuda or not self._fast_path_ok(cell, periodic, node_mask, kvectors):
             return super().forward(charges, cell, positions, neighbor_indices, neighbor_distances,
                                    periodic, node_mask, pair_mask, kvectors)
         validate_parameters(charges, cell, positions, neighbor_indices, neighbor_distances,
                             periodic, pair_mask, node_mask, kvectors)
-        if not positions.is_cuda:
-            raise _native.NativeLibraryError(
-                f"`positions` lives on {positions.device}; torchpme_b200 is a CUDA-only implementation "
-                "(no CPU fallback). Move the inputs to a CUDA device."
-            )
         cfg = self._fused_config(cell)
         mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
         return _FusedMeshPotential.apply(charges, positions, neighbor_distances, neighbor_indices,
@@ -304,7 +313,7 @@ class PMECalculator(Calculator):
         mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
         out = torch.empty_like(q)
         g_d = torch.empty(idx.shape[0], dtype=q.dtype, device=q.device)
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(q.device)
         side = _side_stream(q.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -312,13 +321,14 @@ class PMECalculator(Calculator):
             _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
             _native.pair_backward(q, idx, d, None, mask_u8, q, cfg.full_list, cfg.pair_pot,
                                   want_charges=False, want_pairs=True, grad_pairs_out=g_d)
-        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+        tiles = _native.tile_sort(pos, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
         green = _native.make_green(scale=1.0, **cfg.green_args)
         phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
         main.wait_stream(side)
         epi = _native.make_epilogue(q, dc, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume)
         _, dvalues = _native.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=True,
-                                    values_out=out, epilogue=epi)
+                                    values_out=out, epilogue=epi, tiles=tiles)
         g_pos = torch.einsum("ic,icd->id", q, dvalues) * (2.0 * cfg.half_ivolume)
         energy = (out * q).sum()
         return energy, g_pos, g_d, out

@@ -20,15 +20,18 @@ potentials back.  Inside:
   the ranks by the same all-reduce that combines the real-space pair sum, whose pair list is
   cut into ``W`` contiguous chunks;
 * backward mirrors this (the filter is self-adjoint) and ends with one all-reduce of the
-  ``(N, 3 + C)`` position / charge gradients.  The gradient w.r.t. ``neighbor_distances`` is
-  returned for the rank's own pair chunk (zeros elsewhere): summing it over ranks -- like any
-  data-parallel gradient -- gives the full one.
+  ``(N, 3 + C)`` position / charge gradients.  With ``shard_pairs=True`` (replicated pair list)
+  the gradient w.r.t. ``neighbor_distances`` is all-reduced as well, so every returned gradient is
+  the full, replicated one; with ``shard_pairs=False`` every rank passes its own chunk of the pair
+  list and gets the gradient of that chunk.
 
 Collectives per step (forward + backward): 4 exchanges of the half-complex mesh
 (``C nx ny (nz/2+1)`` complex numbers / W per rank each) and 2 all-reduces.
 """
 
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -65,6 +68,21 @@ class SlabLayout:
         per = -(-n_pairs // self.world)
         lo = min(self.rank * per, n_pairs)
         return lo, min(lo + per, n_pairs)
+
+
+#: seconds a rank waits in a device-side peer barrier before it gives up.  A time-out sets the error
+#: flag of the exchange / reducer; the next all-reduce then returns NaN for EVERY element (so a
+#: stalled peer can never produce silently wrong potentials or forces) and ``check()`` raises.
+PEER_TIMEOUT_SECONDS = float(os.environ.get("TPME_PEER_TIMEOUT", "60"))
+
+
+def _exchange_handles(handle: bytes, device, group, world: int):
+    """all-gather of the CUDA IPC handles (device tensors under NCCL, host tensors under gloo)"""
+    on = device if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=on)
+    handles = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(handles, mine, group=group)
+    return [bytes(h.cpu().tolist()) for h in handles]
 
 
 def _ptr(t: torch.Tensor, offset_elems: int = 0) -> int:
@@ -141,15 +159,13 @@ class PeerExchange:
         self._off_x, self._off_t = self._FLAG_BYTES, self._FLAG_BYTES + half
         self.buffer = _native.PeerBuffer(self._FLAG_BYTES + 2 * half, device)
         # exchange the IPC handles and map the peers' buffers
-        mine = torch.tensor(list(self.buffer.handle), dtype=torch.uint8, device=device)
-        handles = [torch.empty_like(mine) for _ in range(w)]
-        dist.all_gather(handles, mine, group=group)
+        handles = _exchange_handles(self.buffer.handle, device, group, w)
         self.peer_base = []
         for p in range(w):
             if p == layout.rank:
                 self.peer_base.append(self.buffer.ptr)
             else:
-                self.peer_base.append(self.buffer.open_peer(bytes(handles[p].cpu().tolist())))
+                self.peer_base.append(self.buffer.open_peer(handles[p]))
         self.esize = esize
         self.hat = self.buffer.as_tensor(self._off_x, (channels, layout.nxl, ny, layout.nzh, 2), dtype)
         self.hat_t = self.buffer.as_tensor(self._off_t, (channels, nx, layout.nyl, layout.nzh, 2), dtype)
@@ -172,7 +188,7 @@ class PeerExchange:
         return self.hat
 
     def _barrier(self):
-        _native.peer_barrier(self.peer_base, self.layout.rank, self.epoch, self.error)
+        _native.peer_barrier(self.peer_base, self.layout.rank, self.epoch, self.error, PEER_TIMEOUT_SECONDS)
 
     def check(self):
         """host-side check of the barrier time-out flag (a device->host read)"""
@@ -235,16 +251,21 @@ class PeerReducer:
         region = (n_max * esize + 16 * world + 255) // 256 * 256
         self._off_in, self._off_out = self._FLAG_BYTES, self._FLAG_BYTES + region
         self.buffer = _native.PeerBuffer(self._FLAG_BYTES + 2 * region, device)
-        mine = torch.tensor(list(self.buffer.handle), dtype=torch.uint8, device=device)
-        handles = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(handles, mine, group=group)
-        self.peer_base = [self.buffer.ptr if p == rank else self.buffer.open_peer(bytes(handles[p].cpu().tolist()))
+        handles = _exchange_handles(self.buffer.handle, device, group, world)
+        self.peer_base = [self.buffer.ptr if p == rank else self.buffer.open_peer(handles[p])
                           for p in range(world)]
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
         self._in = self.buffer.as_tensor(self._off_in, (n_max,), dtype)
         self._out = self.buffer.as_tensor(self._off_out, (n_max,), dtype)
+        self._watched = [self.error]
+        self._nan = torch.full((), float("nan"), dtype=dtype, device=device)
         dist.barrier(group=group)
+
+    def watch(self, error_flag: torch.Tensor) -> None:
+        """also poison the results when this (exchange) barrier flag is set"""
+        if all(error_flag is not f for f in self._watched):
+            self._watched.append(error_flag)
 
     def zeros(self, n: int, dtype, device) -> torch.Tensor:
         assert n <= self.n_max and dtype == self.dtype
@@ -253,11 +274,14 @@ class PeerReducer:
     def all_reduce(self, flat: torch.Tensor) -> torch.Tensor:
         """`flat` is the view handed out by :meth:`zeros`; returns a fresh tensor with the sums"""
         n = flat.numel()
-        _native.peer_barrier(self.peer_base, self.rank, self.epoch, self.error)
+        _native.peer_barrier(self.peer_base, self.rank, self.epoch, self.error, PEER_TIMEOUT_SECONDS)
         _native.peer_allreduce(self.dtype, self.device, [b + self._off_in for b in self.peer_base],
                                [b + self._off_out for b in self.peer_base], self.rank, n)
-        _native.peer_barrier(self.peer_base, self.rank, self.epoch, self.error)
-        return self._out[:n].clone()
+        _native.peer_barrier(self.peer_base, self.rank, self.epoch, self.error, PEER_TIMEOUT_SECONDS)
+        # a barrier that timed out anywhere in this step means partly written buffers: the copy out
+        # of the exchange region doubles as the poisoning (NaN everywhere), no host sync needed
+        failed = self._watched[0] if len(self._watched) == 1 else torch.stack(self._watched).sum()
+        return torch.where(failed != 0, self._nan, self._out[:n])
 
     def check(self):
         code = int(self.error.item())
@@ -323,7 +347,7 @@ class _SlabMeshPotential(torch.autograd.Function):
         out = cfg.reducer.zeros(q.numel(), q.dtype, q.device).view(q.shape)
         cuda = q.is_cuda
         if cuda:
-            main = torch.cuda.current_stream()
+            main = torch.cuda.current_stream(q.device)
             side = _side_stream(q.device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
@@ -373,7 +397,7 @@ class _SlabMeshPotential(torch.autograd.Function):
                     else torch.empty(ctx.n_pairs, dtype=q.dtype, device=q.device)
             g_d_local = g_d[lo:hi] if need_d else None
             if cuda:
-                main = torch.cuda.current_stream()
+                main = torch.cuda.current_stream(q.device)
                 side = _side_stream(q.device)
                 side.wait_stream(main)
                 forked = True
@@ -392,7 +416,7 @@ class _SlabMeshPotential(torch.autograd.Function):
             green = ops.make_green(scale=1.0, **cfg.green_args)
             psi = cfg.filter.apply(rho_g, green)
             if forked:
-                torch.cuda.current_stream().wait_stream(_side_stream(q.device))
+                torch.cuda.current_stream(q.device).wait_stream(_side_stream(q.device))
                 forked = False
             zero_dc = torch.zeros(c, dtype=q.dtype, device=q.device)
             epi = ops.make_epilogue(g, zero_dc, cfg.half_ivolume, 0.0, 0.0,
@@ -406,8 +430,14 @@ class _SlabMeshPotential(torch.autograd.Function):
                 ops.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi, slab=slab,
                            point_list=plist)
         if forked:
-            torch.cuda.current_stream().wait_stream(_side_stream(q.device))
+            torch.cuda.current_stream(q.device).wait_stream(_side_stream(q.device))
         flat = cfg.reducer.all_reduce(flat)
+        if need_d and cfg.shard_pairs and lay.world > 1:
+            # the ranks hold the same replicated pair list and each filled its own chunk: sum the
+            # chunks so that every returned gradient has the same replicated meaning (positions.grad
+            # through differentiable distances is then the full force on every rank).  Callers who
+            # want to avoid this (P,) all-reduce hand each rank its own chunk with shard_pairs=False.
+            dist.all_reduce(g_d, group=cfg.group)
         g_pos = flat[: 3 * n].view(n, 3)
         if need_q:
             g_q = flat[3 * n:].view(n, c)
@@ -491,6 +521,7 @@ class _SlabMixin:
             if self.transport.startswith("p2p") and world > 1:
                 cfg.reducer = PeerReducer(cfg.n_atoms * (3 + n_channels), charges.dtype, charges.device,
                                           self.process_group, world, rank)
+                cfg.reducer.watch(cfg.filter.exchange.error)
             else:
                 cfg.reducer = TorchReducer(self.process_group, world)
             if len(self._slab_cfgs) >= 4:   # a captured graph keeps its own reference (GraphedStep)

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import torch
 
+from . import mesh as _mesh
 from .mesh import set_nan_check
 
 
@@ -38,7 +39,10 @@ class GraphedStep:
         self.aux = torch.cuda.Stream(device=dev)     # side branch of the energy reduction
         self.graph = torch.cuda.CUDAGraph()
         self.stream.wait_stream(torch.cuda.current_stream(dev))
-        set_nan_check(False)  # the eager NaN guard is a host sync and cannot be captured
+        # the eager NaN guard is a host sync: off for the warm-up steps of the capture stream (it skips
+        # itself while capturing), restored afterwards
+        nan_check_before = _mesh._nan_check
+        set_nan_check(False)
         with torch.cuda.stream(self.stream):
             # autograd ties a leaf to the stream it was created on: create them here
             self.charges = charges.detach().clone()
@@ -68,6 +72,7 @@ class GraphedStep:
                     self.host["energy"].copy_(self.energy, non_blocking=True)
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
+        set_nan_check(nan_check_before)
         # exchange buffers of a slab-decomposed calculator are baked into the graph: keep them alive
         self._keepalive = getattr(calculator, "_slab_cfg", None)
 
@@ -81,7 +86,7 @@ class GraphedStep:
         """captured host -> device copies; the pair list goes over the real-space branch"""
         from .calculators import _side_stream
 
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.positions.device)
         side = _side_stream(self.positions.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -102,7 +107,7 @@ class GraphedStep:
         # E = sum_i q_i V_i: its reduction is a side branch of the graph, and the backward is seeded
         # directly with dE/dV = q (a vector-Jacobian product) instead of going through the tape of
         # the multiply + sum -- same numbers, three small kernels fewer on the critical path
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.positions.device)
         self.aux.wait_stream(main)
         with torch.cuda.stream(self.aux):
             energy = (V.detach() * self.charges).sum()

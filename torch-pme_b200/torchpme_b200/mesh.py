@@ -19,7 +19,7 @@ import numpy as np
 import torch
 from torch.autograd.function import once_differentiable
 
-from . import _native
+from . import _cpu, _native
 
 _NORMS = ("ortho", "forward", "backward")
 
@@ -129,10 +129,11 @@ def _kvectors(cell, ns, half_z: bool = True):
 # autograd nodes
 # --------------------------------------------------------------------------------------
 class _StencilConfig:
-    __slots__ = ("r2u", "ns", "nodes", "method")
+    __slots__ = ("r2u", "ns", "nodes", "method", "tiles")
 
-    def __init__(self, r2u, ns, nodes, method):
+    def __init__(self, r2u, ns, nodes, method, tiles=None):
         self.r2u, self.ns, self.nodes, self.method = r2u, tuple(ns), int(nodes), int(method)
+        self.tiles = tiles   # _native.TileSort of the registered points (None: direct kernels)
 
 
 def _r2u_tensor(cell: torch.Tensor, ns) -> torch.Tensor:
@@ -150,7 +151,7 @@ class _Spread(torch.autograd.Function):
         w = weights.detach().contiguous()
         ctx.cfg = cfg
         ctx.save_for_backward(pos, w)
-        return _native.spread(pos, w, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+        return _native.spread(pos, w, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=cfg.tiles)
 
     @staticmethod
     @once_differentiable
@@ -163,9 +164,9 @@ class _Spread(torch.autograd.Function):
         if need_pos or need_r2u:
             g_pos, g_w, g_r2u = _native.gather_vjp(
                 grad_mesh, pos, w, cfg.r2u, cfg.nodes, cfg.method, want_values=need_w,
-                want_grad_r2u=need_r2u)
+                want_grad_r2u=need_r2u, tiles=cfg.tiles)
         elif need_w:
-            g_w, _ = _native.gather(grad_mesh, pos, cfg.r2u, cfg.nodes, cfg.method)
+            g_w, _ = _native.gather(grad_mesh, pos, cfg.r2u, cfg.nodes, cfg.method, tiles=cfg.tiles)
         return (g_pos if need_pos else None), g_w, g_r2u, None
 
 
@@ -179,7 +180,8 @@ class _Gather(torch.autograd.Function):
         need_pos = ctx.needs_input_grad[1]
         need_r2u = ctx.needs_input_grad[2]
         values, dvalues = _native.gather(mesh_c, pos, cfg.r2u, cfg.nodes, cfg.method,
-                                         want_values=True, want_grad=need_pos and not need_r2u)
+                                         want_values=True, want_grad=need_pos and not need_r2u,
+                                         tiles=cfg.tiles)
         ctx.cfg = cfg
         ctx.mesh_shape = mesh_c.shape
         ctx.save_for_backward(pos, dvalues, mesh_c if need_r2u else None)
@@ -194,10 +196,10 @@ class _Gather(torch.autograd.Function):
         g = grad_values.contiguous()
         g_mesh = g_pos = g_r2u = None
         if need_mesh:
-            g_mesh = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
+            g_mesh = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=cfg.tiles)
         if need_r2u:
             g_pos, _, g_r2u = _native.gather_vjp(mesh_c, pos, g, cfg.r2u, cfg.nodes, cfg.method,
-                                                 want_grad_r2u=True)
+                                                 want_grad_r2u=True, tiles=cfg.tiles)
         elif need_pos:
             g_pos = torch.einsum("ic,icd->id", g, dvalues)
         return g_mesh, (g_pos if need_pos else None), g_r2u, None
@@ -268,6 +270,8 @@ class MeshInterpolator(torch.nn.Module):
         self.interpolation_nodes = interpolation_nodes
         self._ns_host = None
         self._points = None
+        self._tiles = None
+        self._torch_stencil = None
         self.cell = None
         self.ns_mesh = None
         self.update(cell, ns_mesh)
@@ -278,8 +282,12 @@ class MeshInterpolator(torch.nn.Module):
         self._dtype, self._device = cell.dtype, cell.device
         self._ns_host = tuple(ns_host)
         self.ns_mesh = None
+        self._tiles = None
+        self._torch_stencil = None
 
     def update(self, cell: torch.Tensor | None = None, ns_mesh: torch.Tensor | None = None) -> None:
+        self._tiles = None
+        self._torch_stencil = None
         if cell is not None:
             if cell.shape != (3, 3):
                 raise ValueError(f"cell of shape {list(cell.shape)} should be of shape (3, 3)")
@@ -321,15 +329,72 @@ class MeshInterpolator(torch.nn.Module):
         if positions.dim() != 2 or positions.shape[1] != 3:
             raise ValueError(f"shape {list(positions.shape)} of `positions` has to be (N, 3)")
         self._points = positions
+        self._tiles = None   # (dtype, TileSort | None) of these points, built at the first use
+        self._torch_stencil = None   # (flat index, weight) of the torch formulation (CPU tensors, inspection)
 
-    def _stencil(self):
+    def _tile_sort(self, dtype, r2u, ns):
+        """the registered points binned by mesh tile (the counterpart of the reference's index tensors)"""
+        if self._tiles is None or self._tiles[0] != dtype:
+            pos = self._points.detach().to(dtype).contiguous()
+            tiles = _native.tile_sort(pos, r2u, ns, self.interpolation_nodes, _native.METHOD_ID[self.method]) \
+                if pos.is_cuda else None
+            self._tiles = (dtype, tiles)
+        return self._tiles[1]
+
+    def _stencil(self, dtype=None):
         if self._points is None:
             raise ValueError("`compute_weights` has to be called before interpolating")
         ns = self._ns()
-        cfg = _StencilConfig(geometry_of(self.cell).r2u(ns), ns, self.interpolation_nodes,
-                             _native.METHOD_ID[self.method])
+        r2u = geometry_of(self.cell).r2u(ns)
+        cfg = _StencilConfig(r2u, ns, self.interpolation_nodes, _native.METHOD_ID[self.method],
+                             self._tile_sort(dtype or self._dtype, r2u, ns))
         r2u_t = _r2u_tensor(self.cell, ns) if self.cell.requires_grad else None
         return cfg, r2u_t
+
+    # ---- torch formulation: CPU tensors, and the reference's inspection attributes ----------------
+    def _stencil_torch(self):
+        if self._points is None:
+            raise ValueError("`compute_weights` has to be called before interpolating")
+        if self._torch_stencil is None:
+            self._torch_stencil = _cpu.stencil(self._points.to(self._dtype), self.cell, self._ns(),
+                                               self.interpolation_nodes, self.method)
+        return self._torch_stencil
+
+    def _node_table(self):
+        """1-D weights (n, N, 3) and node indices (n, N, 3) as the reference stores them (:65-79, 326-359)"""
+        n = self.interpolation_nodes
+        ns = self._ns()
+        pos = self._points.to(self._dtype)
+        ns_t = torch.tensor(ns, dtype=self._dtype, device=self._device)
+        u = (pos @ torch.linalg.inv(self.cell)) * ns_t
+        base = torch.floor(u.detach()) if n % 2 == 0 else torch.round(u.detach())
+        x = u - (base + 0.5) if n % 2 == 0 else u - base
+        w = _cpu._weights_1d(x, n, self.method).permute(2, 0, 1)                       # (n, N, 3)
+        first = base.to(torch.int64) + (1 - (n + 1) // 2)
+        offs = torch.arange(n, device=self._device)
+        idx = (first[None] + offs[:, None, None]) % torch.tensor(ns, device=self._device)   # (n, N, 3)
+        return w, idx
+
+    @property
+    def interpolation_weights(self) -> torch.Tensor:
+        """1-D weights of the registered points, ``(n, N, 3)`` (computed on demand; the kernels never build it)"""
+        return self._node_table()[0]
+
+    def _shifts(self, axis: int) -> torch.Tensor:
+        n = self.interpolation_nodes
+        grids = torch.meshgrid(*[torch.arange(n, device=self._device)] * 3, indexing="ij")
+        return grids[axis].reshape(-1)
+
+    x_shifts = property(lambda self: self._shifts(0))
+    y_shifts = property(lambda self: self._shifts(1))
+    z_shifts = property(lambda self: self._shifts(2))
+
+    def _indices(self, axis: int) -> torch.Tensor:
+        return self._node_table()[1][self._shifts(axis), :, axis]                      # (n^3, N)
+
+    x_indices = property(lambda self: self._indices(0))
+    y_indices = property(lambda self: self._indices(1))
+    z_indices = property(lambda self: self._indices(2))
 
     def points_to_mesh(self, particle_weights: torch.Tensor) -> torch.Tensor:
         if particle_weights.device != self._device:
@@ -341,6 +406,9 @@ class MeshInterpolator(torch.nn.Module):
             raise ValueError(
                 f"`particle_weights` of dimension {particle_weights.dim()} has to be of dimension 2"
             )
+        if not particle_weights.is_cuda:      # device dispatch: CPU tensors use the torch formulation
+            flat, weight = self._stencil_torch()
+            return _cpu.spread(flat, weight, particle_weights.to(self._dtype), self._ns())
         cfg, r2u_t = self._stencil()
         pos = self._points.to(self._dtype)
         return _Spread.apply(pos, particle_weights.to(self._dtype), r2u_t, cfg)
@@ -348,11 +416,14 @@ class MeshInterpolator(torch.nn.Module):
     def mesh_to_points(self, mesh_vals: torch.Tensor) -> torch.Tensor:
         if mesh_vals.dim() != 4:
             raise ValueError(f"`mesh_vals` of dimension {mesh_vals.dim()} has to be of dimension 4")
-        cfg, r2u_t = self._stencil()
-        if tuple(mesh_vals.shape[1:]) != cfg.ns:
+        if tuple(mesh_vals.shape[1:]) != tuple(self._ns()):
             raise ValueError(
-                f"`mesh_vals` of shape {list(mesh_vals.shape)} does not match the mesh {list(cfg.ns)}"
+                f"`mesh_vals` of shape {list(mesh_vals.shape)} does not match the mesh {list(self._ns())}"
             )
+        if not mesh_vals.is_cuda:
+            flat, weight = self._stencil_torch()
+            return _cpu.gather(flat, weight.to(mesh_vals.dtype), mesh_vals)
+        cfg, r2u_t = self._stencil(mesh_vals.dtype)
         return _Gather.apply(mesh_vals, self._points.to(mesh_vals.dtype), r2u_t, cfg)
 
 
@@ -481,6 +552,16 @@ class KSpaceFilter(torch.nn.Module):
             raise ValueError("The real-space mesh is inconsistent with the k-space grid.")
         geom = geometry_of(self.cell)
         scale = self._scale(ns)
+        if not mesh_values.is_cuda:           # device dispatch: CPU tensors use torch.fft with the filter table
+            result = _cpu.kfilter(mesh_values, self._kfilter.to(mesh_values.dtype), scale)
+            if _nan_check and torch.isnan(result).any():
+                raise ValueError(
+                    "NaNs detected in the k-space filter result. This are probably caused "
+                    "by an unsuitable `mesh_spacing`, resulting in a problematic grid of "
+                    f"shape: {list(mesh_values.shape)}. Try adjsuting the grid by using a "
+                    "different `mesh_spacing` value."
+                )
+            return result
         if self._wants_table():
             table = self._kfilter.to(mesh_values.dtype)
             cfg = _FilterConfig(dict(kind=_native.GREEN_TABLE, recip=geom.recip), scale)

@@ -1,5 +1,5 @@
 """
-EXPERIMENTAL -- neighbor list on the GPU.
+Neighbor list on the GPU.
 
 The reference takes ``neighbor_indices`` / ``neighbor_distances`` from the external ``vesin``
 package (tests/helpers.py:240-275, examples/basic-usage.py:166-169); at 1 M atoms that CPU step and
@@ -8,9 +8,10 @@ builds the list on the device with a cell list: atoms are wrapped into the cell,
 between lattice planes and sorted by bin with torch ops (plumbing); the search itself runs in two
 kernels of ``libtorchpme_b200.so`` (count, fill; ``csrc/neighbors_core.h``).
 
-Status: the search loop is validated on the CPU against the brute-force oracle
-(``tests/test_neighbors.py`` compiles the same header for the host); the CUDA launch path has not
-been run on a GPU yet (``TPME_EXPERIMENTAL=1 pytest tests/test_gpu_experimental.py``).
+Validated on a B200 against the brute-force oracle (``tests/test_gpu_neighbors.py``: identical pair
+sets for cubic / triclinic / smaller-than-cutoff cells, half and full lists, fp32 / fp64, slab and open
+boundaries, 1 M atoms) and on the CPU through a host build of the same search loop
+(``tests/test_neighbors.py``).
 """
 
 from __future__ import annotations
@@ -55,7 +56,7 @@ def _native_search(dtype_id, wrapped, wrap_shift, atom_bins, order, bin_start, n
         raise _native.NativeLibraryError(
             f"`positions` lives on {wrapped.device}; torchpme_b200 is a CUDA-only implementation "
             "(no CPU fallback). Move the inputs to a CUDA device.")
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(wrapped.device).cuda_stream)
     with torch.cuda.device(wrapped.device):
         if offsets is None:
             counts = torch.empty(n, dtype=torch.int32, device=wrapped.device)
