@@ -62,6 +62,7 @@ def run(name, shuffle, reps, out):
     n = pos.shape[0]
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
 
+    _native.TILE_SPREAD = "on"
     tiles = _native.TileSort(_native.tile_plan(dtype, ns, 4, method, n), pos, r2u)
     torch.cuda.synchronize()
     plan = tiles.plan

@@ -38,11 +38,12 @@ def test_tiled_kernels_match_oracle_and_direct(ns, triclinic, channels, method, 
     w = torch.tensor(w_np, dtype=dtype, device=dev)
     r2u = CellGeometry(torch.tensor(cell_np)).r2u(ns)
     mid = _native.METHOD_ID[method]
-    _native.TILE_MODE, saved = "on", _native.TILE_MODE
+    saved = _native.TILE_MODE, _native.TILE_SPREAD
+    _native.TILE_MODE = _native.TILE_SPREAD = "on"
     try:
         tiles = _native.tile_sort(pos, r2u, ns, 4, mid)
     finally:
-        _native.TILE_MODE = saved
+        _native.TILE_MODE, _native.TILE_SPREAD = saved
     assert tiles is not None, "this mesh / stencil is covered by the tiled kernels"
     tol = 1e-11 if dtype == torch.float64 else 2e-5
     # the oracle sees the numbers the kernels saw
@@ -87,6 +88,7 @@ def test_tile_shapes(tile, monkeypatch):
     monkeypatch.setenv("TPME_TILE", tile)
     monkeypatch.setattr(_native, "_tile_plans", {})
     monkeypatch.setattr(_native, "TILE_MODE", "on")
+    monkeypatch.setattr(_native, "TILE_SPREAD", "on")
     ns = (32, 64, 128)
     pos_np, w_np, cell_np = _system(20000, 1, True, seed=5, box=40.0)
     pos = torch.tensor(pos_np, dtype=torch.float32, device="cuda")
@@ -112,7 +114,7 @@ def test_tiled_path_is_the_default_for_large_systems_and_falls_back_otherwise():
     from torchpme_b200.mesh import CellGeometry
 
     r2u = CellGeometry(torch.eye(3, dtype=torch.float64) * 10).r2u((32, 32, 32))
-    big = torch.rand(8192, 3, device="cuda") * 10
+    big = torch.rand(_native.TILE_MIN_POINTS, 3, device="cuda") * 10
     small = torch.rand(100, 3, device="cuda") * 10
     if _native.TILE_MODE == "auto":
         assert _native.tile_sort(big, r2u, (32, 32, 32), 4, 0) is not None
@@ -129,6 +131,7 @@ def test_empty_and_single_point():
     ns = (16, 16, 16)
     r2u = CellGeometry(torch.eye(3, dtype=torch.float64) * 8).r2u(ns)
     saved, _native.TILE_MODE = _native.TILE_MODE, "on"
+    saved_spread, _native.TILE_SPREAD = _native.TILE_SPREAD, "on"
     try:
         assert _native.tile_sort(torch.empty(0, 3, device="cuda"), r2u, ns, 4, 0) is None
         one = torch.tensor([[7.9, 0.1, 4.0]], device="cuda", dtype=torch.float64)
@@ -138,4 +141,4 @@ def test_empty_and_single_point():
         assert rel_err(rho, _native.spread(one, w, r2u, ns, 4, 1)) < 1e-13
         assert abs(float(rho.sum()) - 1.0) < 1e-12
     finally:
-        _native.TILE_MODE = saved
+        _native.TILE_MODE, _native.TILE_SPREAD = saved, saved_spread

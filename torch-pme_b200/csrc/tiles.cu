@@ -701,7 +701,7 @@ extern "C" int tpme_tile_plan_make(int dtype, int nx, int ny, int nz, int nodes,
   plan->nzc = nz / plan->zw;
   // footprint: the largest candidate that still gives every SM about two pencils (one resident CTA per
   // SM for the large tiles, so the second pencil hides the flush / load of the first)
-  static const int cand[][2] = {{8, 16}, {8, 8}, {4, 8}, {4, 4}, {2, 4}, {2, 2}};
+  static const int cand[][2] = {{8, 8}, {8, 8}, {4, 8}, {4, 4}, {2, 4}, {2, 2}};
   int tx = 0, ty = 0;
   if (const char* env = getenv("TPME_TILE")) {
     int a = 0, b = 0;

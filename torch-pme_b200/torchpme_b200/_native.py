@@ -264,7 +264,9 @@ def slab_select_points(positions, r2u, ns, nodes: int, slab):
 #: "auto": use the tiled kernels whenever the mesh / stencil is covered and the system is large
 #: enough to pay for the sort; "off": always the direct kernels; "on": tiled whenever covered
 TILE_MODE = os.environ.get("TPME_TILES", "auto")
-TILE_MIN_POINTS = int(os.environ.get("TPME_TILE_MIN_POINTS", "4096"))
+TILE_MIN_POINTS = int(os.environ.get("TPME_TILE_MIN_POINTS", "65536"))
+#: "auto" | "on" | "off": spread through the shared-memory pencils, or the direct kernel over the sorted atoms
+TILE_SPREAD = os.environ.get("TPME_TILE_SPREAD", "auto")
 
 
 class TileSort:
@@ -274,7 +276,8 @@ class TileSort:
     shared by the forward and backward launches of a step.
     """
 
-    __slots__ = ("plan", "bin_start", "rec", "idx", "n_points", "r2u", "dtype", "positions")
+    __slots__ = ("plan", "bin_start", "rec", "idx", "n_points", "r2u", "dtype", "positions", "count",
+                 "spread_tiled")
 
     def __init__(self, plan, positions, r2u):
         lib = load()
@@ -287,6 +290,14 @@ class TileSort:
         key_rank = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
         self.rec = torch.empty((max(n, 1), 4), dtype=positions.dtype, device=dev)
         self.idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        # Where the spread goes.  Measured on B200 (profiles/r02_tiles.md): the shared-memory pencils win
+        # in fp64 and whenever a mesh cell holds >= ~0.1 atoms (c3: 52 -> 46 us, c5: 38 -> 28 us); for
+        # sparse fp32 meshes (c4: 0.06 atoms per cell) the L2 reduction atomics of the direct kernel are
+        # faster (95 vs 118 us), so the spread stays there and only the gathers use the tiles.
+        density = n / float(plan.nx * plan.ny * plan.nz)
+        self.spread_tiled = (positions.dtype == torch.float64 or density >= 0.09) \
+            if TILE_SPREAD == "auto" else TILE_SPREAD == "on"
+        self.count = None
         with _on(positions, "positions"):
             _check(lib.tpme_tile_sort(_dtype_id(positions), ctypes.byref(plan), _dev(positions, "positions"), n,
                                       _mat9(r2u), _dev(counts, "bin_count"),
@@ -365,7 +376,8 @@ def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=
     `tiles` = :class:`TileSort` of `positions`: use the tiled kernel
     """
     if tiles is not None and slab is None:
-        return tile_spread(tiles, weights, method, out=out)
+        if tiles.spread_tiled:
+            return tile_spread(tiles, weights, method, out=out)
     lib = load()
     n, c = weights.shape
     nx, ny, nz = ns
