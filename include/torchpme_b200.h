@@ -251,6 +251,13 @@ int tpme_peer_barrier(void* const* flags_host, int n_ranks, int rank, void* epoc
 int tpme_peer_allreduce(int dtype, void* const* in_host, void* const* out_host, int n_ranks, int rank,
                         int64_t n, void* stream);
 
+/* Same all-reduce through the NVSwitch (NVLS): `multicast_ptr` is the multicast address of a buffer that
+ * all `n_ranks` GPUs of the node have bound (e.g. torch.distributed._symmetric_memory: multicast_ptr of a
+ * rendezvoused allocation), holding every rank's partial sums at the same offset.  Rank r reduces slice
+ * r with multimem.ld_reduce (the switch returns the sum over all copies) and broadcasts it in place
+ * with multimem.st.  16-byte aligned, padded to a multiple of 16 bytes.  Bracket with tpme_peer_barrier. */
+int tpme_multimem_allreduce(int dtype, void* multicast_ptr, int n_ranks, int rank, int64_t n, void* stream);
+
 /* ---- real space -----------------------------------------------------------------------
  * replaces Calculator._compute_rspace (src/torchpme/calculators/calculator.py:43-87) and
  * Potential.sr_from_dist (potentials/potential.py:106-138).

@@ -49,6 +49,7 @@ def main():
         refs[method] = oracle.calculator_step(spec, q64.numpy(), cell64.numpy(), pos64.numpy(), idx_cpu.numpy(),
                                               d64.numpy(), mesh_spacing, 4, method, grad_out=gout64.numpy())
 
+    reducers = set()
     for transport in (("p2p", "p2p-copy") if one_gpu else ("nccl", "p2p", "p2p-copy")):
         for dtype in (torch.float64, torch.float32):
             for method in ("P3M", "Lagrange"):
@@ -69,6 +70,8 @@ def main():
                 ref = refs[method]
                 if transport.startswith("p2p"):
                     calc._slab_cfg.filter.exchange.check()
+                    calc._slab_cfg.reducer.check()
+                    reducers.add(type(calc._slab_cfg.reducer).__name__)
 
                 def err(a, b):
                     return float(np.abs(a.detach().cpu().double().numpy() - b).max() / max(np.abs(b).max(), 1e-300))
@@ -80,6 +83,8 @@ def main():
                     print(json.dumps(dict(transport=transport, dtype=str(dtype).replace("torch.", ""), method=method,
                                           world=world, V=float(errs[0]), dpos=float(errs[1]), dq=float(errs[2]),
                                           dd=float(errs[3]))), flush=True)
+    if rank == 0:
+        print("reducers used:", sorted(reducers), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

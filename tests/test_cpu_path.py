@@ -125,3 +125,22 @@ def test_double_backward_on_cpu():
     loss = (forces ** 2).sum()
     (g_smearing,) = torch.autograd.grad(loss, pot.smearing)
     assert torch.isfinite(g_smearing) and float(g_smearing.abs()) > 0
+
+
+def test_torch_compile_on_cpu():
+    """tests/calculators/test_workflow.py:146-153 on the CPU path (Dynamo + AOT autograd; eager kernels)"""
+    import torchpme_b200 as tp
+
+    pos = torch.tensor([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]], dtype=torch.float64)
+    q = torch.tensor([[1.0], [-1.0]], dtype=torch.float64)
+    cell = torch.eye(3, dtype=torch.float64)
+    idx, d = torch.tensor([[0, 1]]), torch.tensor([0.8660254], dtype=torch.float64)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=0.2), mesh_spacing=0.1).to(torch.float64)
+    ref = calc(q, cell, pos, idx, d)
+    torch._dynamo.reset()
+    compiled = torch.compile(calc, backend="aot_eager")
+    p = pos.clone().requires_grad_(True)
+    out = compiled(q, cell, p, idx, d)
+    assert type(out) is torch.Tensor and torch.allclose(out, ref, atol=1e-12)
+    out.sum().backward()
+    assert torch.isfinite(p.grad).all()

@@ -88,3 +88,42 @@ def test_spline_and_combined_potentials_through_the_generic_routes():
     assert rel_err(V.detach(), V_ref) < 1e-9
     (V * q).sum().backward()
     assert combined.weights.grad is not None and p.grad is not None
+
+
+def test_tuning_timings_measure_device_time():
+    """event-timed TuningTimings: close to the CUDA-graph replayed step time, not to the Python launch overhead"""
+    import torchpme_b200 as tp
+    from torchpme_b200.tuning import TuningTimings
+
+    pos, q, cell, idx, d = rocksalt(16, dtype=torch.float32, device="cuda")
+    calc_fine = tp.P3MCalculator(tp.CoulombPotential(smearing=1.2).to("cuda"), mesh_spacing=float(cell[0, 0]) / 62)
+    calc_coarse = tp.P3MCalculator(tp.CoulombPotential(smearing=1.2).to("cuda"), mesh_spacing=float(cell[0, 0]) / 14)
+    timings = TuningTimings(q, cell, pos, idx, d, n_repeat=4, n_warmup=4, flush_l2=True)
+    t_fine, t_coarse = timings(calc_fine), timings(calc_coarse)
+    assert 0 < t_coarse < 0.05 and 0 < t_fine < 0.05
+    assert t_fine > t_coarse * 0.5      # a 128^3 mesh is not cheaper than a 32^3 one
+
+
+def test_torch_compile_wraps_the_calculator():
+    """tests/calculators/test_workflow.py:146-153: a torch.compile'd calculator runs and returns a tensor"""
+    import torchpme_b200 as tp
+
+    pos, q, cell, idx, d = rocksalt(6, dtype=torch.float32, device="cuda", cutoff=5.0)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=1.0).to("cuda"), mesh_spacing=float(cell[0, 0]) / 14)
+    ref = calc(q, cell, pos, idx, d)
+    # Dynamo + AOT autograd are what touch this package (the kernels sit behind ctypes calls inside
+    # autograd.Function nodes: graph breaks there, eager execution of those frames); Inductor's code
+    # generation only concerns the torch ops around them and depends on the host toolchain
+    for backend in ("aot_eager", "inductor"):
+        torch._dynamo.reset()
+        compiled = torch.compile(calc, backend=backend)
+        p = pos.clone().requires_grad_(True)
+        try:
+            out = compiled(q, cell, p, idx, d)
+        except Exception as exc:      # a missing host compiler for Inductor is not this package's business
+            if backend == "inductor" and "InductorError" in type(exc).__name__:
+                continue
+            raise
+        assert type(out) is torch.Tensor and rel_err(out, ref) < 1e-5
+        (out * q).sum().backward()
+        assert p.grad is not None and torch.isfinite(p.grad).all()

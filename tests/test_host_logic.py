@@ -174,3 +174,21 @@ def test_fused_config_is_host_only_and_cached():
     with pytest.raises(tp.NativeLibraryError, match="CUDA-only"):
         calc.energy_and_gradients(torch.ones(2, 1, dtype=torch.float64), cell, torch.zeros(2, 3, dtype=torch.float64),
                                   torch.zeros(1, 2, dtype=torch.int64), torch.ones(1, dtype=torch.float64))
+
+
+def test_tuning_timings_on_cpu():
+    """TuningTimings (tuning/tuner.py:283-373): same constructor / forward contract, CPU tensors timed on the host"""
+    import torchpme_b200 as tp
+    from torchpme_b200.tuning import TuningTimings
+
+    pos = torch.tensor([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5]], dtype=torch.float64)
+    q = torch.tensor([[1.0], [-1.0]], dtype=torch.float64)
+    cell = torch.eye(3, dtype=torch.float64)
+    idx = torch.tensor([[0, 1]])
+    d = torch.tensor([0.8660254], dtype=torch.float64)
+    timings = TuningTimings(q, cell, pos, idx, d, n_repeat=2, n_warmup=1, run_backward=True)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=0.2), mesh_spacing=0.1).to(torch.float64)
+    seconds = timings(calc)
+    assert isinstance(seconds, float) and 0 < seconds < 10
+    with pytest.raises(ValueError):       # the reference validates the structure in the constructor
+        TuningTimings(q, torch.eye(2, dtype=torch.float64), pos, idx, d)

@@ -119,9 +119,78 @@ peer_allreduce_kernel(PeerPointers in, PeerPointers out, int n_ranks, int64_t be
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// all-reduce (sum) through the NVSwitch (NVLS): `mc` is the MULTICAST address of a buffer that every
+// rank of the node has bound (one multicast object over W symmetric allocations).  Rank r reduces
+// slice r with multimem.ld_reduce -- one load that the switch answers with the sum over all W
+// copies -- and broadcasts the result with multimem.st, which the switch stores into all W copies,
+// in place.  Per element 1 load + 1 store leave the GPU instead of W loads + W stores of the
+// peer-pointer version above, and every rank ends up with the bitwise identical in-switch sum.
+// The caller brackets the kernel with peer barriers.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 multimem_ld_reduce(const float4* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ double multimem_ld_reduce(const double* mc) {
+  double v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(double* mc, double v) {
+  asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(mc), "d"(v) : "memory");
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+multimem_allreduce_kernel(V* mc, int64_t begin, int64_t end) {
+  // [begin, end) in units of V; two independent reductions in flight per thread
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < end; i += 2 * stride) {
+    const V a = multimem_ld_reduce(mc + i);
+    const V b = multimem_ld_reduce(mc + i + stride);
+    multimem_st(mc + i, a);
+    multimem_st(mc + i + stride, b);
+  }
+  if (i < end) multimem_st(mc + i, multimem_ld_reduce(mc + i));
+}
+
 }  // namespace tpme
 
 using namespace tpme;
+
+extern "C" int tpme_multimem_allreduce(int dtype, void* multicast_ptr, int n_ranks, int rank, int64_t n,
+                                       void* stream) {
+  TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 or 1");
+  TPME_REQUIRE(n_ranks > 0 && n_ranks <= TPME_MAX_RANKS && rank >= 0 && rank < n_ranks, "bad rank layout");
+  TPME_REQUIRE(multicast_ptr != nullptr && ((uintptr_t)multicast_ptr % 16) == 0, "multicast address missing / unaligned");
+  TPME_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return 0;
+  const int vec = dtype == 0 ? 4 : 1;                     // float4 / double per multimem operation
+  const int64_t words = (n + vec - 1) / vec;               // the buffer is padded to whole 16-byte words
+  const int64_t per = (words + n_ranks - 1) / n_ranks;
+  const int64_t begin = per * rank < words ? per * rank : words;
+  const int64_t end = begin + per < words ? begin + per : words;
+  if (end <= begin) return 0;
+  int64_t grid = (end - begin + 511) / 512;
+  const int64_t cap = 2ll * num_sms();
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == 0)
+    multimem_allreduce_kernel<float4><<<(unsigned)grid, 256, 0, s>>>((float4*)multicast_ptr, begin, end);
+  else
+    multimem_allreduce_kernel<double><<<(unsigned)grid, 256, 0, s>>>((double*)multicast_ptr, begin, end);
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int tpme_slab_fft_yz(int dtype, int forward, void* real_mesh, void* mesh_hat,
                                 int n_planes, int ny, int nz, void* stream) {

@@ -11,7 +11,7 @@ Coulomb and inverse-power-law potentials, the mesh interpolator and k-space filt
 ``torchpme_b200.GraphedStep`` the CUDA-graph capture of an energy + forces step.
 """
 
-from . import calculators, graphs, lib, mesh, potentials, prefactors  # noqa: F401
+from . import calculators, graphs, lib, mesh, potentials, prefactors, tuning  # noqa: F401
 from ._native import NativeLibraryError, library_path  # noqa: F401
 from .calculators import Calculator, P3MCalculator, PMECalculator
 from .graphs import GraphedStep  # noqa: F401

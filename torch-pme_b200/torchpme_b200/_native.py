@@ -133,6 +133,7 @@ SIGNATURES = {
     "tpme_neighbor_count": ([_i, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.POINTER(_NeighborSearch), _vp, _vp], _i),
     "tpme_neighbor_fill": ([_i, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.POINTER(_NeighborSearch), _vp, _vp, _vp,
                             _vp, _vp], _i),
+    "tpme_multimem_allreduce": ([_i, _vp, _i, _i, _i64, _vp], _i),
     "tpme_peer_allreduce": ([_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i64, _vp], _i),
     "tpme_fft_plan_create": ([ctypes.POINTER(_vp), _i, _i, _i, _i, _i], _i),
     "tpme_fft_plan_destroy": ([_vp], _i),
@@ -742,6 +743,15 @@ def peer_allreduce(dtype, device, in_ptrs, out_ptrs, rank: int, n: int):
     with torch.cuda.device(device):
         _check(lib.tpme_peer_allreduce(0 if dtype == torch.float32 else 1, a, b, w, rank, n, _stream()),
                "tpme_peer_allreduce")
+    _count()
+
+
+def multimem_allreduce(dtype, device, multicast_ptr: int, world: int, rank: int, n: int):
+    """in-switch (NVLS) sum all-reduce of n reals behind a multicast address (call between two peer barriers)"""
+    lib = load()
+    with torch.cuda.device(device):
+        _check(lib.tpme_multimem_allreduce(0 if dtype == torch.float32 else 1, _vp(int(multicast_ptr)), world, rank, n,
+                                           _stream()), "tpme_multimem_allreduce")
     _count()
 
 

@@ -289,6 +289,89 @@ class PeerReducer:
             raise RuntimeError(f"peer barrier timed out waiting for rank {code - 1}")
 
 
+class MulticastReducer:
+    """
+    Sum all-reduce through the NVSwitch (NVLS, ``tpme_multimem_allreduce``): the partial results of all
+    ranks sit at the same offset of a symmetric allocation that is bound to ONE multicast address
+    (``torch.distributed._symmetric_memory`` provides allocation and rendezvous -- plumbing); rank r
+    reduces slice r with ``multimem.ld_reduce`` (the switch returns the sum over all GPUs) and broadcasts
+    it in place with ``multimem.st``.  Same interface and barrier protocol as :class:`PeerReducer`.
+    Raises ``RuntimeError`` when the node has no multicast support (the caller falls back).
+    """
+
+    _FLAG_BYTES = 256
+
+    def __init__(self, n_max: int, dtype, device, group, world: int, rank: int):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank, self.dtype, self.device = world, rank, dtype, device
+        esize = 4 if dtype == torch.float32 else 8
+        self.n_max = n_max
+        self._flag_elems = self._FLAG_BYTES // esize
+        region = (n_max * esize + 16 * world + 255) // 256 * 256
+        self._buf = symm_mem.empty(self._flag_elems + region // esize, dtype=dtype, device=device)
+        pg = group if group is not None else dist.group.WORLD
+        self._handle = symm_mem.rendezvous(self._buf, pg.group_name)
+        mc = int(getattr(self._handle, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("no multicast (NVLS) support on this node")
+        self._mc_data = mc + self._FLAG_BYTES
+        self.peer_base = [int(p) for p in self._handle.buffer_ptrs]
+        self._buf.zero_()
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        self._watched = [self.error]
+        self._nan = torch.full((), float("nan"), dtype=dtype, device=device)
+        self._data = self._buf[self._flag_elems:]
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+
+    def watch(self, error_flag: torch.Tensor) -> None:
+        if all(error_flag is not f for f in self._watched):
+            self._watched.append(error_flag)
+
+    def zeros(self, n: int, dtype, device) -> torch.Tensor:
+        assert n <= self.n_max and dtype == self.dtype
+        return self._data[:n].zero_()
+
+    def all_reduce(self, flat: torch.Tensor) -> torch.Tensor:
+        n = flat.numel()
+        _native.peer_barrier(self.peer_base, self.rank, self.epoch, self.error, PEER_TIMEOUT_SECONDS)
+        _native.multimem_allreduce(self.dtype, self.device, self._mc_data, self.world, self.rank, n)
+        _native.peer_barrier(self.peer_base, self.rank, self.epoch, self.error, PEER_TIMEOUT_SECONDS)
+        failed = self._watched[0] if len(self._watched) == 1 else torch.stack(self._watched).sum()
+        return torch.where(failed != 0, self._nan, self._data[:n])
+
+    def check(self):
+        code = int(self.error.item())
+        if code:
+            raise RuntimeError(f"peer barrier timed out waiting for rank {code - 1}")
+
+
+def make_reducer(n_max: int, dtype, device, group, world: int, rank: int, kind: str = "auto"):
+    """
+    peer-memory reducer of the p2p transports: NVLS multicast when the node supports it (all ranks
+    agree through one tiny all-reduce), plain peer pointers otherwise.  TPME_SLAB_REDUCER = auto |
+    multimem | peer overrides.
+    """
+    kind = os.environ.get("TPME_SLAB_REDUCER", kind)
+    reducer = None
+    if kind in ("auto", "multimem") and dist.get_backend(group) == "nccl":
+        try:
+            reducer = MulticastReducer(n_max, dtype, device, group, world, rank)
+        except Exception:
+            if kind == "multimem":
+                raise
+            reducer = None
+        ok = torch.tensor([1 if reducer is not None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok) == 0:
+            reducer = None
+    if reducer is None:
+        reducer = PeerReducer(n_max, dtype, device, group, world, rank)
+    return reducer
+
+
 class SlabFilter:
     """``irfft3(G * rfft3(.))`` of a mesh distributed as x slabs (buffers reused across calls)."""
 
@@ -519,8 +602,8 @@ class _SlabMixin:
                                     self.process_group, self.transport, ops)
             cfg.n_atoms = charges.shape[0]
             if self.transport.startswith("p2p") and world > 1:
-                cfg.reducer = PeerReducer(cfg.n_atoms * (3 + n_channels), charges.dtype, charges.device,
-                                          self.process_group, world, rank)
+                cfg.reducer = make_reducer(cfg.n_atoms * (3 + n_channels), charges.dtype, charges.device,
+                                           self.process_group, world, rank)
                 cfg.reducer.watch(cfg.filter.exchange.error)
             else:
                 cfg.reducer = TorchReducer(self.process_group, world)
