@@ -293,3 +293,39 @@ def test_graphed_step_matches_eager():
         (gp2,) = torch.autograd.grad(e2, (p2,))
         assert rel_err(graphed_io.host["energy"], e2.detach()) < 1e-5
         assert rel_err(graphed_io.host["grad_positions"], gp2) < 1e-4
+
+
+def test_cluster_plane_fft_matches_torch_fft():
+    """
+    The two-CTA cluster (y,z)-plane kernels for 256 x 256 fp32 planes (half a plane per CTA, exchange
+    through distributed shared memory; opt-in with TPME_FFT_CLUSTER=1) against torch.fft, in a fresh
+    process because the switch is read once.
+    """
+    import os
+    import subprocess
+    import sys
+
+    code = """
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from torchpme_b200 import _native
+from torchpme_b200.mesh import geometry_of
+ns = (16, 256, 256)
+gen = torch.Generator().manual_seed(3)
+cell = (torch.eye(3, dtype=torch.float64) * 9.0 + 0.7 * torch.rand(3, 3, generator=gen, dtype=torch.float64)).cuda()
+geom = geometry_of(cell)
+mesh = torch.randn((2,) + ns, generator=gen, dtype=torch.float64).cuda()
+plan = _native.get_plan(torch.float32, ns, 2, mesh.device)
+assert _native.load().tpme_fft_plan_uses_own_fft(plan.handle) == 3
+green = _native.make_green(_native.GREEN_COULOMB, 0.37, geom.recip, geom.spacing(ns), smearing=1.1, prefactor=1.3, p3m_nodes=4)
+table = _native.green_table(torch.float64, ns, green, mesh.device)
+ref = torch.fft.irfftn(torch.fft.rfftn(mesh, dim=(1, 2, 3)) * table, s=ns, dim=(1, 2, 3), norm="forward")
+out, _ = _native.kfilter_apply(mesh.float(), green)
+err = float((out.double() - ref).abs().max() / ref.abs().max())
+print("cluster fft rel err", err)
+assert err < 2e-5
+""" % (os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "torch-pme_b200"),
+       os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, TPME_FFT_CLUSTER="1"),
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]

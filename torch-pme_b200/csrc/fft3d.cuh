@@ -21,6 +21,7 @@
 //   * G(k) is evaluated from per-CTA axis tables (k = a[ix] + b[iy,iz], sines by angle addition),
 //     one exp and one division per k-point.
 #pragma once
+#include <cooperative_groups.h>
 #include <cstdlib>
 #include <cstring>
 #include "common.cuh"
@@ -803,6 +804,233 @@ plane_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int rows_per
 }
 
 // ---------------------------------------------------------------------------------------
+// fused (y, z) plane transforms for planes that do not fit one SM (256 x 256 in fp32: the half-complex
+// plane is 264 KB): a thread-block CLUSTER of two CTAs shares the plane, CTA h holding the rows
+// [h NY/2, (h+1) NY/2) in its shared memory.  The z pass, the split and the contiguous-row radix group
+// of the y pass work on local rows; the strided radix group of the y pass needs rows of both halves:
+// the CTAs split the columns between them and read / write the partner's rows through DISTRIBUTED
+// SHARED MEMORY (8 of the 16 operands of every item), bracketed by cluster barriers.  One global read
+// and one global write per plane instead of the two round trips of the separate z / y passes.
+// ---------------------------------------------------------------------------------------
+template <typename T, int NY, int NZ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPlaneMaxThreads)
+plane2_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int rows_per_chunk) {
+  namespace cg = cooperative_groups;
+  constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1, RLOC = NY / 2;
+  using CZ = Chain<H>;
+  using CY = Chain<NY>;
+  static_assert(CZ::NG == 2 && CY::NG == 2, "the cluster plane kernels use two radix groups per axis");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C2<T>* plane = reinterpret_cast<C2<T>*>(smem_raw);      // [RLOC][P]: the rows of this CTA
+  C2<T>* buf1 = plane + (size_t)RLOC * P;
+  C2<T>* twz = buf1 + (size_t)rows_per_chunk * P1;
+  C2<T>* twy = twz + NZ / 2;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int half = (int)cluster.block_rank();
+  const int plane_id = blockIdx.x >> 1;
+  C2<T>* other = cluster.map_shared_rank(plane, half ^ 1);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  fill_twiddles<T, NZ>(twz, tid, nt);
+  fill_twiddles<T, NY>(twy, tid, nt);
+  __syncthreads();
+  const C2<T>* in2 = reinterpret_cast<const C2<T>*>(in) + ((int64_t)plane_id * NY + half * RLOC) * H;
+  // ---- z pass of the local rows (packed half-length DIF, natural order into the plane) --------
+  constexpr int QAz = H / CZ::RA, RL = CZ::RL;
+  for (int row0 = 0; row0 < RLOC; row0 += rows_per_chunk) {
+    const int rows = min(rows_per_chunk, RLOC - row0);
+    for (int w = tid; w < rows * QAz; w += nt) {
+      const int r = w / QAz, j0 = w - r * QAz;
+      C2<T> v[CZ::RA];
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) v[i] = in2[(row0 + r) * H + j0 + i * QAz];
+      dif_regs<T, H, H, CZ::RA, -1, 2>(v, j0, twz);
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) buf1[r * P1 + skew(j0 + i * QAz)] = v[i];
+    }
+    __syncthreads();
+    for (int w = tid; w < rows * (H / RL); w += nt) {
+      const int r = w / (H / RL), blk = w - r * (H / RL);
+      C2<T> v[RL];
+#pragma unroll
+      for (int i = 0; i < RL; ++i) v[i] = buf1[r * P1 + skew(blk * RL + i)];
+      dif_regs<T, H, RL, RL, -1, 2>(v, 0, twz);
+#pragma unroll
+      for (int i = 0; i < RL; ++i) plane[(row0 + r) * P + bitrev<H>(blk * RL + i)] = v[i];
+    }
+    __syncthreads();
+  }
+  // ---- split in place (local rows) --------------------------------------------------------------
+  for (int i = tid; i < RLOC * (H / 2 + 1); i += nt) {
+    const int r = i / (H / 2 + 1), k = i - r * (H / 2 + 1);
+    C2<T>* row = plane + r * P;
+    if (k == 0) {
+      const C2<T> z0 = row[0];
+      row[0] = {z0.x + z0.y, T(0)};
+      row[H] = {z0.x - z0.y, T(0)};
+    } else {
+      const int kk = H - k;
+      const C2<T> zk = row[k], zkk = row[kk];
+      const C2<T> w = twz[k];
+      {
+        const C2<T> s = {T(0.5) * (zk.x + zkk.x), T(0.5) * (zk.y - zkk.y)};
+        const C2<T> d = {T(0.5) * (zk.x - zkk.x), T(0.5) * (zk.y + zkk.y)};
+        const C2<T> wd = cmul(d, w);
+        row[k] = {s.x + wd.y, s.y - wd.x};
+      }
+      if (kk != k) {
+        const C2<T> s = {T(0.5) * (zkk.x + zk.x), T(0.5) * (zkk.y - zk.y)};
+        const C2<T> d = {T(0.5) * (zkk.x - zk.x), T(0.5) * (zkk.y + zk.y)};
+        const C2<T> wd = {-(d.x * w.x + d.y * w.y), -(d.y * w.x - d.x * w.y)};
+        row[kk] = {s.x + wd.y, s.y - wd.x};
+      }
+    }
+  }
+  cluster.sync();     // both halves of the plane are complete
+  // ---- y pass, strided radix group: rows j0 + i QAy live in both CTAs; this CTA takes half of the columns
+  constexpr int QAy = NY / CY::RA, RA = CY::RA;
+  const int c0 = half == 0 ? 0 : (P + 1) / 2, c1 = half == 0 ? (P + 1) / 2 : P, ncol = c1 - c0;
+  for (int w = tid; w < ncol * QAy; w += nt) {
+    const int j0 = w / ncol, c = c0 + (w - j0 * ncol);
+    C2<T> v[RA];
+#pragma unroll
+    for (int i = 0; i < RA; ++i) {
+      const int r = j0 + i * QAy;                       // compile-time owner: rows < RLOC belong to CTA 0
+      C2<T>* base = ((i * QAy >= RLOC) == (half == 1)) ? plane : other;
+      v[i] = base[(r & (RLOC - 1)) * P + c];
+    }
+    dif_regs<T, NY, NY, RA, -1, 1>(v, j0, twy);
+#pragma unroll
+    for (int i = 0; i < RA; ++i) {
+      const int r = j0 + i * QAy;
+      C2<T>* base = ((i * QAy >= RLOC) == (half == 1)) ? plane : other;
+      base[(r & (RLOC - 1)) * P + c] = v[i];
+    }
+  }
+  cluster.sync();     // the partner has finished reading / writing this CTA's rows
+  // ---- y pass, contiguous radix group on the local rows; bit reversal folded into the global row index
+  C2<T>* o = out + (int64_t)plane_id * NY * P;
+  constexpr int RLy = CY::RL;
+  for (int w = tid; w < P * (RLOC / RLy); w += nt) {
+    const int blk = w / P, c = w - blk * P;
+    C2<T> v[RLy];
+#pragma unroll
+    for (int i = 0; i < RLy; ++i) v[i] = plane[(blk * RLy + i) * P + c];
+    dif_regs<T, NY, RLy, RLy, -1, 1>(v, 0, twy);
+#pragma unroll
+    for (int i = 0; i < RLy; ++i) o[bitrev<NY>(half * RLOC + blk * RLy + i) * P + c] = v[i];
+  }
+}
+
+template <typename T, int NY, int NZ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPlaneMaxThreads)
+plane2_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int rows_per_chunk) {
+  namespace cg = cooperative_groups;
+  constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1, RLOC = NY / 2;
+  using CZ = Chain<H>;
+  using CY = Chain<NY>;
+  static_assert(CZ::NG == 2 && CY::NG == 2, "the cluster plane kernels use two radix groups per axis");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C2<T>* plane = reinterpret_cast<C2<T>*>(smem_raw);
+  C2<T>* buf1 = plane + (size_t)RLOC * P;
+  C2<T>* twz = buf1 + (size_t)rows_per_chunk * P1;
+  C2<T>* twy = twz + NZ / 2;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int half = (int)cluster.block_rank();
+  const int plane_id = blockIdx.x >> 1;
+  C2<T>* other = cluster.map_shared_rank(plane, half ^ 1);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  fill_twiddles<T, NZ>(twz, tid, nt);
+  fill_twiddles<T, NY>(twy, tid, nt);
+  __syncthreads();
+  const C2<T>* src = in + (int64_t)plane_id * NY * P;
+  // ---- y pass, contiguous DIT group into the local rows (bit-reversed row order read from global) ----
+  constexpr int RLy = CY::RL, QAy = NY / CY::RA, RA = CY::RA;
+  for (int w = tid; w < P * (RLOC / RLy); w += nt) {
+    const int blk = w / P, c = w - blk * P;
+    C2<T> v[RLy];
+#pragma unroll
+    for (int i = 0; i < RLy; ++i) v[i] = src[bitrev<NY>(half * RLOC + blk * RLy + i) * P + c];
+    dit_regs<T, NY, 1, RLy, +1, 1>(v, 0, twy);
+#pragma unroll
+    for (int i = 0; i < RLy; ++i) plane[(blk * RLy + i) * P + c] = v[i];
+  }
+  cluster.sync();
+  // ---- y pass, strided DIT group over the rows of both CTAs (this CTA: half of the columns) ----------
+  const int c0 = half == 0 ? 0 : (P + 1) / 2, c1 = half == 0 ? (P + 1) / 2 : P, ncol = c1 - c0;
+  for (int w = tid; w < ncol * QAy; w += nt) {
+    const int j0 = w / ncol, c = c0 + (w - j0 * ncol);
+    C2<T> v[RA];
+#pragma unroll
+    for (int i = 0; i < RA; ++i) {
+      const int r = j0 + i * QAy;
+      C2<T>* base = ((i * QAy >= RLOC) == (half == 1)) ? plane : other;
+      v[i] = base[(r & (RLOC - 1)) * P + c];
+    }
+    dit_regs<T, NY, QAy, RA, +1, 1>(v, j0, twy);
+#pragma unroll
+    for (int i = 0; i < RA; ++i) {
+      const int r = j0 + i * QAy;
+      C2<T>* base = ((i * QAy >= RLOC) == (half == 1)) ? plane : other;
+      base[(r & (RLOC - 1)) * P + c] = v[i];
+    }
+  }
+  cluster.sync();
+  // ---- un-split in place (local rows) ---------------------------------------------------------------
+  for (int i = tid; i < RLOC * (H / 2 + 1); i += nt) {
+    const int r = i / (H / 2 + 1), k = i - r * (H / 2 + 1);
+    C2<T>* row = plane + r * P;
+    if (k == 0) {
+      const T x0 = row[0].x, xh = row[H].x;
+      row[0] = {x0 + xh, x0 - xh};
+    } else {
+      const int kk = H - k;
+      const C2<T> xk = row[k], xkk = row[kk];
+      const C2<T> w = twz[k];
+      {
+        const C2<T> s = {xk.x + xkk.x, xk.y - xkk.y};
+        const C2<T> d = {xk.x - xkk.x, xk.y + xkk.y};
+        const C2<T> wd = {d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y};
+        row[k] = {s.x - wd.y, s.y + wd.x};
+      }
+      if (kk != k) {
+        const C2<T> s = {xkk.x + xk.x, xkk.y - xk.y};
+        const C2<T> d = {xkk.x - xk.x, xkk.y + xk.y};
+        const C2<T> wd = {-(d.x * w.x - d.y * w.y), -(d.x * w.y + d.y * w.x)};
+        row[kk] = {s.x - wd.y, s.y + wd.x};
+      }
+    }
+  }
+  __syncthreads();
+  // ---- z pass of the local rows (packed half-length DIT) -----------------------------------------------
+  C2<T>* o = reinterpret_cast<C2<T>*>(out) + ((int64_t)plane_id * NY + half * RLOC) * H;
+  constexpr int RLz = CZ::RL, QAz = H / CZ::RA;
+  for (int row0 = 0; row0 < RLOC; row0 += rows_per_chunk) {
+    const int rows = min(rows_per_chunk, RLOC - row0);
+    for (int w = tid; w < rows * (H / RLz); w += nt) {
+      const int r = w / (H / RLz), blk = w - r * (H / RLz);
+      C2<T> v[RLz];
+#pragma unroll
+      for (int i = 0; i < RLz; ++i) v[i] = plane[(row0 + r) * P + bitrev<H>(blk * RLz + i)];
+      dit_regs<T, H, 1, RLz, +1, 2>(v, 0, twz);
+#pragma unroll
+      for (int i = 0; i < RLz; ++i) buf1[r * P1 + skew(blk * RLz + i)] = v[i];
+    }
+    __syncthreads();
+    for (int w = tid; w < rows * QAz; w += nt) {
+      const int r = w / QAz, j0 = w - r * QAz;
+      C2<T> v[CZ::RA];
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) v[i] = buf1[r * P1 + skew(j0 + i * QAz)];
+      dit_regs<T, H, QAz, CZ::RA, +1, 2>(v, j0, twz);
+#pragma unroll
+      for (int i = 0; i < CZ::RA; ++i) o[(row0 + r) * H + j0 + i * QAz] = v[i];
+    }
+    __syncthreads();
+  }
+  cluster.sync();     // no CTA exits while the partner may still touch its shared memory
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 inline bool supported_dim(int n) { return n >= 8 && n <= 512 && (n & (n - 1)) == 0; }
@@ -934,8 +1162,49 @@ int launch_plane(bool forward, const void* in, void* out, int n_planes, cudaStre
   return 0;
 }
 
+// two-CTA cluster variant: half of the plane per CTA
+template <typename T, int NY, int NZ>
+int launch_plane2(bool forward, const void* in, void* out, int n_planes, cudaStream_t s) {
+  constexpr int H = NZ / 2, P = H + 1, P1 = H + (H >> 4) + 1, RLOC = NY / 2;
+  constexpr int items_per_row = H / Chain<H>::RA > 0 ? H / Chain<H>::RA : 1;
+  const int threads = kPlaneMaxThreads;
+  int rows = threads / items_per_row;
+  if (rows > RLOC) rows = RLOC;
+  auto smem_of = [&](int r) { return ((size_t)RLOC * P + (size_t)r * P1 + NZ / 2 + NY / 2) * sizeof(C2<T>); };
+  while (rows > 1 && smem_of(rows) > 216 * 1024) rows >>= 1;
+  const size_t smem = smem_of(rows);
+  if (smem > 216 * 1024) return -1;
+  if (forward) {
+    if (int rc = allow_smem(plane2_r2c_kernel<T, NY, NZ>, smem)) return rc;
+    plane2_r2c_kernel<T, NY, NZ><<<2 * n_planes, threads, smem, s>>>((const T*)in, (C2<T>*)out, rows);
+  } else {
+    if (int rc = allow_smem(plane2_c2r_kernel<T, NY, NZ>, smem)) return rc;
+    plane2_c2r_kernel<T, NY, NZ><<<2 * n_planes, threads, smem, s>>>((const C2<T>*)in, (T*)out, rows);
+  }
+  TPME_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T> struct ClusterPlane {   // which planes go to the two-CTA kernels
+  static int run(int, int, bool, const void*, void*, int, cudaStream_t) { return -1; }
+};
+template <> struct ClusterPlane<float> {
+  static int run(int ny, int nz, bool forward, const void* in, void* out, int n_planes, cudaStream_t s) {
+    // opt-in (TPME_FFT_CLUSTER=1): measured on B200 at 256^3 (profiles/r02_summary.md) the two cluster
+    // kernels take 77 us each against 69 / 87 us of the separate z / y passes they replace -- no gain yet
+    static const bool off = [] { const char* e = getenv("TPME_FFT_CLUSTER"); return !(e && e[0] == '1'); }();
+    if (off) return -1;
+    if (ny == 256 && nz == 256) return launch_plane2<float, 256, 256>(forward, in, out, n_planes, s);
+    return -1;
+  }
+};
+
 template <typename T>
 int dispatch_plane(int ny, int nz, bool forward, const void* in, void* out, int n_planes, cudaStream_t s) {
+  {
+    const int rc = ClusterPlane<T>::run(ny, nz, forward, in, out, n_planes, s);
+    if (rc >= 0) return rc;
+  }
 #define TPME_PLANE(A, B) if (ny == A && nz == B) return launch_plane<T, A, B>(forward, in, out, n_planes, s);
   TPME_PLANE(16, 16) TPME_PLANE(32, 32) TPME_PLANE(64, 64) TPME_PLANE(128, 128)
   TPME_PLANE(32, 16) TPME_PLANE(16, 32) TPME_PLANE(64, 32) TPME_PLANE(32, 64) TPME_PLANE(128, 64) TPME_PLANE(64, 128)

@@ -152,7 +152,10 @@ extern "C" int tpme_fft_plan_uses_own_fft(tpme_fft_plan plan) {
   if (plan == nullptr || !plan->own_fft) return 0;
   auto listed = [](int n) { return n == 16 || n == 32 || n == 64 || n == 128; };
   const int ny = plan->ny, nz = plan->nz;
-  const bool fused = listed(ny) && listed(nz) && (ny == nz || ny == 2 * nz || nz == 2 * ny);
+  bool fused = listed(ny) && listed(nz) && (ny == nz || ny == 2 * nz || nz == 2 * ny);
+  // 256 x 256 fp32 planes: the two-CTA cluster kernels (half a plane per CTA, exchange through DSMEM)
+  static const bool cluster_off = [] { const char* e = getenv("TPME_FFT_CLUSTER"); return !(e && e[0] == '1'); }();
+  if (plan->dtype == 0 && ny == 256 && nz == 256 && !cluster_off) fused = true;
   return fused ? 3 : 5;
 }
 
