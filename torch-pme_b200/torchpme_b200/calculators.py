@@ -9,6 +9,9 @@ CPU path (a CPU tensor raises ``NativeLibraryError``).
 
 from __future__ import annotations
 
+import weakref
+from typing import Optional
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -16,6 +19,39 @@ from . import _cpu, _native
 from ._checks import validate_parameters
 from .mesh import KSpaceFilter, MeshInterpolator, P3MKSpaceFilter, geometry_of
 from .potentials import Potential
+
+
+# --------------------------------------------------------------------------------------
+# TorchScript boundary.  ``torch.jit.script(calculator)`` (and ``jit.save`` / ``jit.load``, which the
+# reference's tests/calculators/test_workflow.py:130-162 exercise) compiles ``forward``; everything behind
+# it here is ctypes + autograd.Function code that TorchScript cannot compile.  ``forward`` is therefore a
+# scriptable shell: eagerly it calls ``_forward_impl`` directly, under TorchScript it calls the operator
+# ``torchpme_b200::calculator_forward`` registered below with the PyTorch dispatcher, which looks the
+# live calculator up by its handle and runs the same ``_forward_impl`` -- as a CompositeImplicitAutograd
+# kernel, so the autograd nodes of the implementation are recorded on the tape as usual.  A scripted
+# calculator is thus a shell around a dispatcher operator that needs this package (and the calculator it
+# was scripted from) in the same process; it does not make the module deployable without Python.
+# --------------------------------------------------------------------------------------
+_CALCULATORS: "weakref.WeakValueDictionary[int, Calculator]" = weakref.WeakValueDictionary()
+_OPS = torch.library.Library("torchpme_b200", "DEF")
+_OPS.define("calculator_forward(Tensor charges, Tensor cell, Tensor positions, Tensor neighbor_indices, "
+            "Tensor neighbor_distances, Tensor? periodic, Tensor? node_mask, Tensor? pair_mask, "
+            "Tensor? kvectors, int handle) -> Tensor")
+
+
+def _calculator_forward_op(charges, cell, positions, neighbor_indices, neighbor_distances, periodic,
+                           node_mask, pair_mask, kvectors, handle):
+    calc = _CALCULATORS.get(int(handle))
+    if calc is None:
+        raise RuntimeError(
+            "torchpme_b200::calculator_forward: the calculator this scripted module was created from is "
+            "not alive in this process (a scripted torchpme_b200 calculator is a shell around the Python "
+            "implementation, see torchpme_b200/calculators.py)")
+    return calc._forward_impl(charges, cell, positions, neighbor_indices, neighbor_distances, periodic,
+                              node_mask, pair_mask, kvectors)
+
+
+_OPS.impl("calculator_forward", _calculator_forward_op, "CompositeImplicitAutograd")
 
 
 class _PairSum(torch.autograd.Function):
@@ -162,7 +198,10 @@ class Calculator(torch.nn.Module):
             raise TypeError(f"Potential must be an instance of Potential, got {type(potential)}")
         self.potential = potential
         self.full_neighbor_list = full_neighbor_list
+        self._handle: int = id(self)
+        _CALCULATORS[self._handle] = self
 
+    @torch.jit.unused
     def _compute_rspace(self, charges, neighbor_indices, neighbor_distances, pair_mask=None):
         pot = self.potential
         mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
@@ -193,11 +232,24 @@ class Calculator(torch.nn.Module):
         return _PairSum.apply(charges, bare.to(charges.dtype), neighbor_indices, mask_u8,
                               native_pot, self.full_neighbor_list)
 
+    @torch.jit.unused
     def _compute_kspace(self, charges, cell, positions, periodic=None, node_mask=None, kvectors=None):
         raise NotImplementedError(f"`compute_kspace` not implemented for {self.__class__.__name__}")
 
-    def forward(self, charges, cell, positions, neighbor_indices, neighbor_distances,
-                periodic=None, node_mask=None, pair_mask=None, kvectors=None):
+    def forward(self, charges: torch.Tensor, cell: torch.Tensor, positions: torch.Tensor,
+                neighbor_indices: torch.Tensor, neighbor_distances: torch.Tensor,
+                periodic: Optional[torch.Tensor] = None, node_mask: Optional[torch.Tensor] = None,
+                pair_mask: Optional[torch.Tensor] = None, kvectors: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not torch.jit.is_scripting():
+            return self._forward_impl(charges, cell, positions, neighbor_indices, neighbor_distances,
+                                      periodic, node_mask, pair_mask, kvectors)
+        return torch.ops.torchpme_b200.calculator_forward(
+            charges, cell, positions, neighbor_indices, neighbor_distances, periodic, node_mask, pair_mask,
+            kvectors, self._handle)
+
+    @torch.jit.unused
+    def _forward_impl(self, charges, cell, positions, neighbor_indices, neighbor_distances,
+                      periodic=None, node_mask=None, pair_mask=None, kvectors=None):
         validate_parameters(charges, cell, positions, neighbor_indices, neighbor_distances,
                             periodic, pair_mask, node_mask, kvectors)
         potential_sr = self._compute_rspace(charges, neighbor_indices, neighbor_distances, pair_mask)
@@ -242,13 +294,14 @@ class PMECalculator(Calculator):
             return False
         return not any(t.requires_grad for t in list(pot.parameters()) + list(pot.buffers()))
 
-    def forward(self, charges, cell, positions, neighbor_indices, neighbor_distances,
-                periodic=None, node_mask=None, pair_mask=None, kvectors=None):
+    @torch.jit.unused
+    def _forward_impl(self, charges, cell, positions, neighbor_indices, neighbor_distances,
+                      periodic=None, node_mask=None, pair_mask=None, kvectors=None):
         # the fused node is CUDA only; CPU tensors go through the modular blocks, which dispatch to the
         # torch formulation of _cpu.py (CUDA tensors never do)
         if not positions.is_cuda or not self._fast_path_ok(cell, periodic, node_mask, kvectors):
-            return super().forward(charges, cell, positions, neighbor_indices, neighbor_distances,
-                                   periodic, node_mask, pair_mask, kvectors)
+            return super()._forward_impl(charges, cell, positions, neighbor_indices, neighbor_distances,
+                                         periodic, node_mask, pair_mask, kvectors)
         validate_parameters(charges, cell, positions, neighbor_indices, neighbor_distances,
                             periodic, pair_mask, node_mask, kvectors)
         cfg = self._fused_config(cell)

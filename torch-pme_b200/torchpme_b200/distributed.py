@@ -549,8 +549,9 @@ class _SlabMixin:
             raise RuntimeError("torch.distributed has to be initialised for the slab-decomposed calculators")
         return dist.get_world_size(self.process_group), dist.get_rank(self.process_group)
 
-    def forward(self, charges, cell, positions, neighbor_indices, neighbor_distances,
-                periodic=None, node_mask=None, pair_mask=None, kvectors=None):
+    @torch.jit.unused
+    def _forward_impl(self, charges, cell, positions, neighbor_indices, neighbor_distances,
+                      periodic=None, node_mask=None, pair_mask=None, kvectors=None):
         if node_mask is not None or kvectors is not None:
             raise NotImplementedError("Batching not implemented for mesh-based calculators")
         if periodic is not None:

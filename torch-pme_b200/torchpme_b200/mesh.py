@@ -255,6 +255,11 @@ class MeshInterpolator(torch.nn.Module):
     stencils (reference: ``lib/mesh_interpolator.py:4-457``).
     """
 
+    # TorchScript (a calculator that owns an interpolator can be scripted, see calculators.py): nothing of
+    # this class is compiled -- it has no forward, and its properties are host-side / inspection code
+    __jit_unused_properties__ = ["inverse_cell", "interpolation_weights", "x_shifts", "y_shifts", "z_shifts",
+                                 "x_indices", "y_indices", "z_indices"]
+
     def __init__(self, cell: torch.Tensor, ns_mesh: torch.Tensor, interpolation_nodes: int, method: str):
         super().__init__()
         allowed = {"Lagrange": (3, 4, 5, 6, 7), "P3M": (1, 2, 3, 4, 5)}
@@ -458,6 +463,8 @@ class KSpaceFilter(torch.nn.Module):
     with differentiable torch ops.
     """
 
+    __jit_unused_properties__ = ["_kvectors", "_k_sq", "_kfilter"]
+
     def __init__(self, cell, ns_mesh, kernel, fft_norm: str = "ortho", ifft_norm: str = "ortho"):
         super().__init__()
         if fft_norm not in _NORMS:
@@ -538,6 +545,12 @@ class KSpaceFilter(torch.nn.Module):
         return any(t.requires_grad for t in list(self.kernel.parameters()) + list(self.kernel.buffers()))
 
     def forward(self, mesh_values: torch.Tensor) -> torch.Tensor:
+        if torch.jit.is_scripting():
+            raise RuntimeError("KSpaceFilter is not available under TorchScript: script the calculator that owns it")
+        return self._forward_impl(mesh_values)
+
+    @torch.jit.unused
+    def _forward_impl(self, mesh_values: torch.Tensor) -> torch.Tensor:
         if mesh_values.dim() != 4:
             raise ValueError(
                 f"`mesh_values` needs to be a 4 dimensional tensor, got {mesh_values.dim()}"
