@@ -281,6 +281,17 @@ class MeshInterpolator(torch.nn.Module):
         self.ns_mesh = None
         self.update(cell, ns_mesh)
 
+    def _apply(self, fn, *args, **kwargs):
+        """`.to()` / `.cuda()` also move the geometry tensors this module holds as plain attributes"""
+        super()._apply(fn, *args, **kwargs)
+        if self.cell is not None:
+            self.cell = fn(self.cell)
+            self._dtype, self._device = self.cell.dtype, self.cell.device
+        if self.ns_mesh is not None:
+            self.ns_mesh = fn(self.ns_mesh)
+        self._points = self._tiles = self._torch_stencil = None
+        return self
+
     # the calculators already know ns on the host and skip the tensor round trip
     def _update_host(self, cell: torch.Tensor, ns_host: tuple):
         self.cell = cell
@@ -477,6 +488,16 @@ class KSpaceFilter(torch.nn.Module):
         self.ns_mesh = None
         self._table = None
         self.update(cell, ns_mesh)
+
+    def _apply(self, fn, *args, **kwargs):
+        """`.to()` / `.cuda()` also move the geometry tensors this module holds as plain attributes"""
+        super()._apply(fn, *args, **kwargs)
+        if getattr(self, "cell", None) is not None:
+            self.cell = fn(self.cell)
+        if self.ns_mesh is not None:
+            self.ns_mesh = fn(self.ns_mesh)
+        self._table = None
+        return self
 
     # ---- geometry -------------------------------------------------------------------------
     def _update_host(self, cell: torch.Tensor, ns_host: tuple):
