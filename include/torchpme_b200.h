@@ -117,11 +117,14 @@ typedef struct tpme_tile_plan {
   int nx, ny, nz, nodes;
   int tx, ty, zw;             /* pencil footprint (first stencil nodes) and z chunk width */
   int npx, npy, nzc;          /* pencils per axis, z chunks per pencil */
+  int nzt, gather_nzt;        /* z tiles per pencil of the spread / of the gather: one CTA per (pencil, z tile) */
   int n_bins;                 /* npx * npy * nzc */
-  int row_stride, plane_stride; /* shared-memory tile strides in elements */
+  int row_stride, plane_stride; /* shared-memory row stride of the spread tile in elements (informational) */
   int smem_bytes;
   int spread_threads, gather_threads;
   int spread_batch;            /* atoms a warp of the spread fetches and stages at a time (16 or 32) */
+  int spread_tiled;            /* 1: tpme_tile_spread is the faster spread for this case; 0: use tpme_spread
+                                  (the plan then has one bin per pencil and serves the gathers only) */
 } tpme_tile_plan;
 int tpme_tile_plan_make(int dtype, int nx, int ny, int nz, int nodes, int method, int64_t n_points,
                         tpme_tile_plan* plan_host);

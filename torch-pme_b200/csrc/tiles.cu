@@ -39,18 +39,24 @@ struct TileGeom {
   int nodes;
   int tx_shift, ty_shift, zw_shift;   // pencil footprint / z chunk width (powers of two)
   int npx, npy, nzc;                  // pencils per axis, z chunks per pencil
+  int nzt, tz, nzc_t;                 // z tiles per pencil, first-node z extent of a tile, z chunks per tile
   int rows_x, rows_y;                 // tile rows: tx + nodes - 1, ty + nodes - 1
   int sy, sx;                         // row / plane stride of the shared-memory tile in elements
 };
 
-static TileGeom geom_of(const tpme_tile_plan& p) {
+// geometry for a kernel that cuts the pencils into `nzt` z tiles (the spread and the gather choose
+// their own: the bins are z chunks of zw planes, any tile extent that is a multiple of zw works)
+static TileGeom geom_of(const tpme_tile_plan& p, int nzt) {
   TileGeom g;
   g.nx = p.nx; g.ny = p.ny; g.nz = p.nz; g.nodes = p.nodes;
   auto log2i = [](int v) { int s = 0; while ((1 << s) < v) ++s; return s; };
   g.tx_shift = log2i(p.tx); g.ty_shift = log2i(p.ty); g.zw_shift = log2i(p.zw);
   g.npx = p.npx; g.npy = p.npy; g.nzc = p.nzc;
+  g.nzt = nzt; g.tz = p.nz / nzt; g.nzc_t = p.nzc / nzt;
   g.rows_x = p.tx + p.nodes - 1; g.rows_y = p.ty + p.nodes - 1;
-  g.sy = p.row_stride; g.sx = p.plane_stride;
+  g.sy = g.tz + 4;                                  // = 4 (mod 32): the 4 y rows of a stencil hit different banks
+  const int raw = g.rows_y * g.sy;                  // multiple of 4 elements
+  g.sx = raw + ((16 - raw % 32) + 32) % 32;         // = 16 (mod 32): the two x planes of a warp access too
   return g;
 }
 
@@ -282,11 +288,12 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
   // per-warp staging area: `batch` atoms x 13 words (12 one-dimensional weights + tile offset)
   T* st_rec = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ctrl) + 256) + (threadIdx.x >> 5) * (kStageWords * batch);
 
-  const int pencil = blockIdx.x;
-  const int bin0 = pencil * g.nzc;
-  const int p_begin = bin_start[bin0], p_end = bin_start[bin0 + g.nzc];
+  const int pencil = blockIdx.x / g.nzt, zt = blockIdx.x - pencil * g.nzt;
+  const int bin0 = pencil * g.nzc + zt * g.nzc_t;
+  const int p_begin = bin_start[bin0], p_end = bin_start[bin0 + g.nzc_t];
   if (p_begin == p_end) return;                 // nothing lands here: the mesh was zeroed by the caller
   const int px = pencil / g.npy, py = pencil - px * g.npy;
+  const int z_lo = zt * g.tz;                   // first-node z of this tile: [z_lo, z_lo + tz)
   const int lane = threadIdx.x & 31;
   const int la = lane >> 4, lb = (lane >> 2) & 3, lc = lane & 3;
   T* const lane_ptr = tile + (la * g.sx + lb * g.sy + lc);
@@ -303,13 +310,13 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
   int s1, mid, e2;
   {
     int* cs = reinterpret_cast<int*>(tile);          // chunk starts, parked in the (not yet used) tile
-    for (int k = threadIdx.x; k <= g.nzc; k += blockDim.x) cs[k] = bin_start[bin0 + k];
+    for (int k = threadIdx.x; k <= g.nzc_t; k += blockDim.x) cs[k] = bin_start[bin0 + k];
     __syncthreads();
     if (warp == 0) {
       int bound = 0;
       if (lane < n_warps) {                          // first chunk whose start reaches this warp's share
         const int target = p_begin + (int)(((int64_t)(p_end - p_begin) * lane) / n_warps);
-        int lo = 0, hi = g.nzc;
+        int lo = 0, hi = g.nzc_t;
         while (lo < hi) {
           const int m = (lo + hi) >> 1;
           if (cs[m] < target) lo = m + 1; else hi = m;
@@ -319,10 +326,10 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
       // at least two chunks per warp (first chunks of neighbouring warps must not be adjacent)
       for (int w = 1; w < n_warps; ++w) {
         const int prev = __shfl_sync(0xffffffffu, bound, w - 1);
-        if (lane == w) bound = min(max(bound, prev + 2), g.nzc - 2 * (n_warps - w));
+        if (lane == w) bound = min(max(bound, prev + 2), g.nzc_t - 2 * (n_warps - w));
       }
       if (lane < n_warps) ctrl[lane] = bound;
-      if (lane == 0) ctrl[n_warps] = g.nzc;
+      if (lane == 0) ctrl[n_warps] = g.nzc_t;
     }
     __syncthreads();
     const int c0 = ctrl[warp], c1 = ctrl[warp + 1];
@@ -362,8 +369,9 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
           if (lane < cnt) {
             // The lane that fetched an atom evaluates its 12 one-dimensional weights ONCE and parks them
             // (13 words per atom, odd stride: conflict free) -- the 32 lanes that accumulate the atom then
-            // only pick wx[a], wx[a + 2], q wy[b], wz[c] and the tile offset.  first_z + c may run into
-            // the 4 pad elements behind a row (folded back to z = 0..2 before the flush): no wrap here.
+            // only pick wx[a], wx[a + 2], q wy[b], wz[c] and the tile offset.  Rows hold tz + 4 elements:
+            // first_z + c may run into the 3 halo elements behind the tile's own z range (flushed to the
+            // next z tile / wrapped to z = 0 by a second bulk reduction): no wrap in the loop.
             T w[3][4], dw[3][4];
             if (method == TPME_P3M) {
 #pragma unroll
@@ -379,7 +387,7 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
               st[4 + k] = w[1][k] * pq;
               st[8 + k] = w[2][k];
             }
-            const int base = (pr.packed & 31) * g.sx + ((pr.packed >> 5) & 31) * g.sy + (pr.packed >> 10);
+            const int base = (pr.packed & 31) * g.sx + ((pr.packed >> 5) & 31) * g.sy + ((pr.packed >> 10) - z_lo);
             reinterpret_cast<int*>(st + 12)[0] = base;
           }
           __syncwarp();
@@ -413,29 +421,26 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
       if (e2 > mid) run_range(e2, e2);
     }
     __syncthreads();
-    // periodic wrap along z: what landed in the pad behind a row belongs to its first elements
-    {
-      const int rows = g.rows_x * g.rows_y;
-      for (int i = threadIdx.x; i < rows * 3; i += blockDim.x) {
-        const int r = i / 3, k = i - 3 * r;
-        const int rx = r / g.rows_y, ry = r - rx * g.rows_y;
-        T* row = tile + rx * g.sx + ry * g.sy;
-        row[k] += row[g.nz + k];
-      }
-    }
-    // flush: one bulk reduction (add) per tile row into the global mesh, periodic wrap per row
+    // flush: two bulk reductions (add) per tile row into the global mesh -- the tile's own z range and
+    // the 3 halo elements behind it (+ 1 zero pad: 16 / 32 bytes), which belong to the next z tile or,
+    // for the last one, wrap to z = 0; periodic wrap in x, y per row
     fence_proxy_async_smem();
     __syncthreads();
     if (!(debug & 2)) {
       T* dst = mesh + ch * mesh_size;
       const int rows = g.rows_x * g.rows_y;
-      const uint32_t row_bytes = (uint32_t)(g.nz * sizeof(T));
+      const uint32_t main_bytes = (uint32_t)(g.tz * sizeof(T)), halo_bytes = (uint32_t)(4 * sizeof(T));
       const int gx0 = px << g.tx_shift, gy0 = py << g.ty_shift;
+      int z_hi = z_lo + g.tz;
+      z_hi -= z_hi >= g.nz ? g.nz : 0;
       for (int r = threadIdx.x; r < rows; r += blockDim.x) {
         const int rx = r / g.rows_y, ry = r - rx * g.rows_y;
         int gx = gx0 + rx; gx -= gx >= g.nx ? g.nx : 0;
         int gy = gy0 + ry; gy -= gy >= g.ny ? g.ny : 0;
-        bulk_reduce_add<T>(dst + ((int64_t)gx * g.ny + gy) * g.nz, tile + rx * g.sx + ry * g.sy, row_bytes);
+        T* grow = dst + ((int64_t)gx * g.ny + gy) * g.nz;
+        const T* srow = tile + rx * g.sx + ry * g.sy;
+        bulk_reduce_add<T>(grow + z_lo, srow, main_bytes);
+        bulk_reduce_add<T>(grow + z_hi, srow + g.tz, halo_bytes);
       }
       bulk_commit();
       bulk_wait_read_all();   // the tile is re-zeroed (next channel) / freed (exit) only after the reads
@@ -463,15 +468,18 @@ tile_gather4_kernel(const T* __restrict__ mesh, const T* __restrict__ sorted_rec
   uint64_t* bar = reinterpret_cast<uint64_t*>(tile + tile_elems);
   __shared__ T red[9][16];
 
-  const int pencil = blockIdx.x;
-  const int bin0 = pencil * g.nzc;
-  const int p_begin = bin_start[bin0], p_end = bin_start[bin0 + g.nzc];
+  const int pencil = blockIdx.x / g.nzt, zt = blockIdx.x - pencil * g.nzt;
+  const int bin0 = pencil * g.nzc + zt * g.nzc_t;
+  const int p_begin = bin_start[bin0], p_end = bin_start[bin0 + g.nzc_t];
   const bool with_r2u = (MODE & 4) && grad_r2u != nullptr;
   if (p_begin == p_end) return;
   const int px = pencil / g.npy, py = pencil - px * g.npy;
+  const int z_lo = zt * g.tz;
+  int z_hi = z_lo + g.tz;
+  z_hi -= z_hi >= g.nz ? g.nz : 0;
   const int64_t mesh_size = (int64_t)g.nx * g.ny * g.nz;
   const int rows = g.rows_x * g.rows_y;
-  const uint32_t row_bytes = (uint32_t)(g.nz * sizeof(T));
+  const uint32_t main_bytes = (uint32_t)(g.tz * sizeof(T)), halo_bytes = (uint32_t)(4 * sizeof(T));
   const bool with_extra = (MODE & 4) && epi.enabled && epi.coef2 != nullptr;
 
   if (threadIdx.x == 0) mbar_init(bar, 1);
@@ -482,7 +490,7 @@ tile_gather4_kernel(const T* __restrict__ mesh, const T* __restrict__ sorted_rec
 
   for (int ch = 0; ch < n_channels; ++ch) {
     if (ch > 0) __syncthreads();   // everybody is done reading the previous channel's tile
-    if (threadIdx.x == 0 && !(debug & 2)) mbar_expect_tx(bar, row_bytes * (uint32_t)rows);
+    if (threadIdx.x == 0 && !(debug & 2)) mbar_expect_tx(bar, (main_bytes + halo_bytes) * (uint32_t)rows);
     __syncthreads();
     if (!(debug & 2)) {
       const T* src = mesh + ch * mesh_size;
@@ -491,7 +499,10 @@ tile_gather4_kernel(const T* __restrict__ mesh, const T* __restrict__ sorted_rec
         const int rx = r / g.rows_y, ry = r - rx * g.rows_y;
         int gx = gx0 + rx; gx -= gx >= g.nx ? g.nx : 0;
         int gy = gy0 + ry; gy -= gy >= g.ny ? g.ny : 0;
-        bulk_load(tile + rx * g.sx + ry * g.sy, src + ((int64_t)gx * g.ny + gy) * g.nz, row_bytes, bar);
+        const T* grow = src + ((int64_t)gx * g.ny + gy) * g.nz;
+        T* srow = tile + rx * g.sx + ry * g.sy;
+        bulk_load(srow, grow + z_lo, main_bytes, bar);            // the tile's own z range ...
+        bulk_load(srow + g.tz, grow + z_hi, halo_bytes, bar);     // ... and the halo behind it (next tile / wrap)
       }
     }
     // first atom of this thread: its record travels while the tile is still arriving
@@ -502,15 +513,6 @@ tile_gather4_kernel(const T* __restrict__ mesh, const T* __restrict__ sorted_rec
       i_next = __ldg(sorted_idx + p_begin + threadIdx.x);
     }
     if (!(debug & 2)) mbar_wait(bar, (uint32_t)(ch & 1));
-    // periodic wrap along z: copy the first elements of every row into the pad behind it
-    for (int i = threadIdx.x; i < rows * 3; i += blockDim.x) {
-      const int r = i / 3, k = i - 3 * r;
-      const int rx = r / g.rows_y, ry = r - rx * g.rows_y;
-      T* row = tile + rx * g.sx + ry * g.sy;
-      row[g.nz + k] = row[k];
-    }
-    __syncthreads();
-
     for (int j = p_begin + threadIdx.x; j < p_end && !(debug & 1); j += blockDim.x) {
       // the record / index of this thread's NEXT atom are fetched before the current one is gathered
       const Rec<T> r = r_next;
@@ -528,7 +530,7 @@ tile_gather4_kernel(const T* __restrict__ mesh, const T* __restrict__ sorted_rec
 #pragma unroll
       for (int a = 0; a < 3; ++a) Stencil<METHOD, N>::template eval<T, DERIV>(r.x[a], w[a], dw[a]);
       const int lx = r.packed & 31, ly = (r.packed >> 5) & 31, fz = r.packed >> 10;
-      const T* base = tile + lx * g.sx + ly * g.sy + fz;
+      const T* base = tile + lx * g.sx + ly * g.sy + (fz - z_lo);
       T val = T(0), du0 = T(0), du1 = T(0), du2 = T(0);
 #pragma unroll
       for (int a = 0; a < N; ++a) {
@@ -624,14 +626,6 @@ static int max_smem_optin() {
   return cached;
 }
 
-static void fill_strides(tpme_tile_plan* p, int elem) {
-  (void)elem;
-  p->row_stride = p->nz + 4;                       // = 4 (mod 32): the 4 y rows of a stencil hit different banks
-  const int rows_y = p->ty + p->nodes - 1;
-  const int raw = rows_y * p->row_stride;          // multiple of 4 elements
-  p->plane_stride = raw + ((16 - raw % 32) + 32) % 32;   // = 16 (mod 32): the two x planes of a warp access too
-}
-
 template <typename T, int METHOD, int MODE>
 static int launch_tile_gather(const tpme_tile_plan* plan, const void* mesh, const void* rec, const int* idx,
                               const int* bin_start, const void* positions, const void* coef, int n_channels,
@@ -650,7 +644,7 @@ static int launch_tile_gather(const tpme_tile_plan* plan, const void* mesh, cons
     epi.add_coef = epi.dc = epi.coef2 = epi.dvalues2 = nullptr;
     epi.scale = epi.self_half = epi.background = epi.vjp_scale = T(0);
   }
-  const TileGeom g = geom_of(*plan);
+  const TileGeom g = geom_of(*plan, plan->gather_nzt);
   const size_t smem = (size_t)g.rows_x * g.sx * sizeof(T) + 16;
   auto kernel = tile_gather4_kernel<T, METHOD, MODE>;
   static thread_local bool configured = false;
@@ -661,7 +655,7 @@ static int launch_tile_gather(const tpme_tile_plan* plan, const void* mesh, cons
                                       max_smem_optin() - (int)attr.sharedSizeBytes));
     configured = true;
   }
-  kernel<<<(unsigned)(g.npx * g.npy), plan->gather_threads, smem, stream>>>(
+  kernel<<<(unsigned)(g.npx * g.npy * g.nzt), plan->gather_threads, smem, stream>>>(
       (const T*)mesh, (const T*)rec, idx, bin_start, (const T*)positions, (const T*)coef, n_channels,
       load_mat3<T>(r2u), g, (T*)values, (T*)dvalues, (T*)grad_positions, accumulate, (T*)grad_r2u, epi,
       getenv("TPME_TILE_DEBUG") ? atoi(getenv("TPME_TILE_DEBUG")) : 0);
@@ -697,11 +691,16 @@ extern "C" int tpme_tile_plan_make(int dtype, int nx, int ny, int nz, int nodes,
   if (!is_pow2(nx) || !is_pow2(ny) || !is_pow2(nz) || nz < 8 || nz > 32768 || nx < 4 || ny < 4) return 3;
   if (n_points <= 0 || n_points >= (1ll << 31)) return 3;
   plan->nx = nx; plan->ny = ny; plan->nz = nz; plan->nodes = nodes;
-  plan->zw = 4;                                    // >= nodes - 1: chunks of equal parity never overlap
-  plan->nzc = nz / plan->zw;
-  // footprint: the largest candidate that still gives every SM about two pencils (one resident CTA per
-  // SM for the large tiles, so the second pencil hides the flush / load of the first)
-  static const int cand[][2] = {{8, 8}, {8, 8}, {4, 8}, {4, 4}, {2, 4}, {2, 2}};
+  // The tiled spread is the faster spread on every measured workload once the pencils are cut into z
+  // tiles (profiles/r02_summary.md: c3 52 -> 33 us, c5 38 -> 20 us, c4 95 -> 77 us); TPME_TILE_SPREAD = off
+  // keeps the direct kernel (the plan then has one bin per gather tile and serves the gathers only).
+  plan->spread_tiled = 1;
+  if (const char* env = getenv("TPME_TILE_SPREAD")) {
+    if (strcmp(env, "off") == 0) plan->spread_tiled = 0;
+  }
+  // footprint of a pencil in first stencil nodes.  (8, 8) is the measured optimum of the B200 sweeps
+  // (profiles/r02_summary.md); smaller meshes take the largest footprint that still gives every SM a pencil.
+  static const int cand[][2] = {{8, 8}, {4, 8}, {4, 4}, {2, 4}, {2, 2}};
   int tx = 0, ty = 0;
   if (const char* env = getenv("TPME_TILE")) {
     int a = 0, b = 0;
@@ -709,47 +708,66 @@ extern "C" int tpme_tile_plan_make(int dtype, int nx, int ny, int nz, int nodes,
   }
   const int smem_cap = max_smem_optin() - 2048;   // static shared memory of the gather + slack
   const int sms = num_sms();
-  // spread warps: every warp needs at least two z chunks; up to 32 warps in fp32 (64 registers), 16 in fp64
-  int max_warps = dtype == 0 ? 32 : 16;
-  if (const char* env = getenv("TPME_TILE_WARPS")) {
-    const int v = atoi(env);
-    if (v >= 1 && v <= max_warps) max_warps = v;
-  }
-  int warps0 = plan->nzc / 2;
-  if (warps0 > max_warps) warps0 = max_warps;
-  if (warps0 < 1) warps0 = 1;
-  // staging areas of the spread's warps: 32 atoms per batch, 16 when the tile leaves no room
-  auto stage_bytes_of = [&](int w, int batch) { return w * kStageWords * batch * elem; };
-  auto tile_bytes = [&](int a, int b) {
-    const int rows_y = b + nodes - 1;
-    const size_t raw = (size_t)rows_y * (nz + 4);
-    return (size_t)(a + nodes - 1) * (raw + ((16 - raw % 32) + 32) % 32) * elem + 256;
-  };
-  if (tx == 0) {
-    for (int k = 0; k < 6 && tx == 0; ++k) {
-      const int a = cand[k][0], b = cand[k][1];
-      if (a > nx || b > ny) continue;
-      if ((int64_t)(tile_bytes(a, b) + stage_bytes_of(warps0 > 16 ? 16 : warps0, 16)) > smem_cap) continue;
-      if ((int64_t)(nx / a) * (ny / b) >= sms || k == 5) { tx = a; ty = b; }
-    }
-    if (tx == 0) { tx = nx < 2 ? nx : 2; ty = ny < 2 ? ny : 2; }
+  for (int k = 0; k < 5 && tx == 0; ++k) {
+    const int a = cand[k][0], b = cand[k][1];
+    if (a > nx || b > ny) continue;
+    if ((int64_t)(nx / a) * (ny / b) >= sms || k == 4) { tx = a; ty = b; }
   }
   if (tx > nx || ty > ny) return 3;
   plan->tx = tx; plan->ty = ty;
   plan->npx = nx / tx; plan->npy = ny / ty;
+  // z tiles: the pencil is cut along z until a tile (+ the staging areas of the spread) is small enough for
+  // several CTAs per SM -- then one CTA accumulates while another one zeroes / flushes / loads its tile.
+  // A tile keeps >= 16 first-node planes (>= 4 z chunks).  TPME_TILE_NZT overrides.
+  const int rows = (tx + nodes - 1) * (ty + nodes - 1);
+  auto stage_bytes_of = [&](int w, int batch) { return (size_t)w * kStageWords * batch * elem; };
+  auto tile_bytes = [&](int nzt) {
+    const size_t raw = (size_t)(ty + nodes - 1) * (nz / nzt + 4);
+    return (size_t)(tx + nodes - 1) * (raw + ((16 - raw % 32) + 32) % 32) * elem + 256;
+  };
+  auto warps_of = [&](int nzt) {
+    int max_warps = dtype == 0 ? 32 : 16;
+    if (const char* env = getenv("TPME_TILE_WARPS")) {
+      const int v = atoi(env);
+      if (v >= 1 && v <= max_warps) max_warps = v;
+    }
+    int w = (nz / nzt / 4) / 2;                  // every warp needs at least two z chunks of 4 planes
+    if (w > max_warps) w = max_warps;
+    if (w > 16 && nzt > 1) w = 16;
+    const double per_tile = (double)n_points / ((double)plan->npx * plan->npy * nzt);
+    while (w > 2 && per_tile < 16.0 * w) w >>= 1;
+    return w < 1 ? 1 : w;
+  };
+  // spread: tiles of 32 first-node planes (8 z chunks): 4 .. 8 tiles per SM; gather: the whole pencil when it
+  // fits (its tile load is two bulk copies per row and z tile: fewer, longer copies win there)
+  int nzt = nz / 32 > 0 ? nz / 32 : 1;
+  if (const char* env = getenv("TPME_TILE_NZT")) {
+    const int v = atoi(env);
+    if (is_pow2(v) && nz / v >= 8) nzt = v;
+  }
+  int gather_nzt = 1;
+  while (nz / (2 * gather_nzt) >= 8 && (int64_t)tile_bytes(gather_nzt) > smem_cap) gather_nzt *= 2;
+  if (const char* env = getenv("TPME_TILE_GATHER_NZT")) {
+    const int v = atoi(env);
+    if (is_pow2(v) && nz / v >= 8) gather_nzt = v;
+  }
+  if ((int64_t)tile_bytes(gather_nzt) > smem_cap) return 3;
+  plan->nzt = nzt;
+  plan->gather_nzt = gather_nzt;
+  plan->zw = plan->spread_tiled ? 4 : nz / gather_nzt;   // >= nodes - 1: only adjacent chunks overlap
+  plan->nzc = nz / plan->zw;
   plan->n_bins = plan->npx * plan->npy * plan->nzc;
-  fill_strides(plan, elem);
-  const double per_pencil = (double)n_points / ((double)plan->npx * plan->npy);
-  int warps = warps0;
-  while (warps > 2 && per_pencil < 16.0 * warps) warps >>= 1;
-  // the most warps / the largest batch the tile leaves room for
-  while (warps > 1 && (int64_t)(tile_bytes(tx, ty) + stage_bytes_of(warps, 16)) > smem_cap) warps >>= 1;
+  plan->row_stride = nz / nzt + 4;
+  plan->plane_stride = 0;
+  int warps = warps_of(nzt);
+  while (warps > 1 && (int64_t)(tile_bytes(nzt) + stage_bytes_of(warps, 16)) > smem_cap) warps >>= 1;
   plan->spread_threads = 32 * warps;
-  plan->spread_batch = (int64_t)(tile_bytes(tx, ty) + stage_bytes_of(warps, 32)) <= smem_cap ? 32 : 16;
-  plan->smem_bytes = (int)(tile_bytes(tx, ty) + stage_bytes_of(warps, plan->spread_batch));
+  plan->spread_batch = (int64_t)(tile_bytes(nzt) + stage_bytes_of(warps, 32)) <= smem_cap ? 32 : 16;
+  plan->smem_bytes = (int)(tile_bytes(nzt) + stage_bytes_of(warps, plan->spread_batch));
   if (plan->smem_bytes > smem_cap) return 3;
+  const double per_tile = (double)n_points / ((double)plan->npx * plan->npy * gather_nzt);
   int gt = 64;
-  while (gt < 512 && gt < per_pencil) gt <<= 1;
+  while (gt < 512 && gt < per_tile) gt <<= 1;
   plan->gather_threads = gt;
   return 0;
 }
@@ -762,7 +780,7 @@ extern "C" int tpme_tile_sort(int dtype, const tpme_tile_plan* plan, const void*
   TPME_REQUIRE(n_points >= 0 && n_points < (1ll << 31), "the tiled kernels hold 32-bit point indices");
   TPME_REQUIRE(((uintptr_t)sorted_rec % 16) == 0 && ((uintptr_t)key_rank % 8) == 0, "workspace alignment");
   cudaStream_t s = (cudaStream_t)stream;
-  const TileGeom g = geom_of(*plan);
+  const TileGeom g = geom_of(*plan, plan->nzt);
   TPME_CUDA_OK(cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)plan->n_bins, s));
   const unsigned grid = (unsigned)((n_points + 255) / 256);
   if (n_points > 0) {
@@ -793,6 +811,8 @@ extern "C" int tpme_tile_spread(int dtype, const tpme_tile_plan* plan, const voi
                                 int64_t n_points, int n_channels, int method, void* mesh, int accumulate,
                                 void* stream) {
   TPME_REQUIRE(plan != nullptr && plan->n_bins > 0 && plan->nodes == 4, "invalid tile plan");
+  TPME_REQUIRE(plan->spread_tiled && plan->zw == 4 && plan->nzc / plan->nzt >= 2,
+               "this tile plan was made without z chunks (spread_tiled = 0)");
   TPME_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (float32) or 1 (float64)");
   TPME_REQUIRE(method == TPME_P3M || method == TPME_LAGRANGE, "unknown interpolation method");
   TPME_REQUIRE(((uintptr_t)mesh % 16) == 0, "mesh must be 16-byte aligned");
@@ -801,10 +821,10 @@ extern "C" int tpme_tile_spread(int dtype, const tpme_tile_plan* plan, const voi
   if (!accumulate)
     TPME_CUDA_OK(cudaMemsetAsync(mesh, 0, elem * (size_t)n_channels * plan->nx * plan->ny * plan->nz, s));
   if (n_points == 0 || n_channels == 0) return 0;
-  const TileGeom g = geom_of(*plan);
+  const TileGeom g = geom_of(*plan, plan->nzt);
   const size_t smem = (size_t)g.rows_x * g.sx * elem + 256 +
                       (size_t)(plan->spread_threads / 32) * kStageWords * plan->spread_batch * elem;
-  const unsigned grid = (unsigned)(g.npx * g.npy);
+  const unsigned grid = (unsigned)(g.npx * g.npy * g.nzt);
   const int dbg = getenv("TPME_TILE_DEBUG") ? atoi(getenv("TPME_TILE_DEBUG")) : 0;
   if (dtype == 0) {
     static thread_local bool configured = false;

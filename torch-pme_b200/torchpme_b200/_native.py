@@ -83,8 +83,8 @@ class _NeighborSearch(ctypes.Structure):
 
 class _TilePlan(ctypes.Structure):
     _fields_ = [(name, ctypes.c_int) for name in (
-        "nx", "ny", "nz", "nodes", "tx", "ty", "zw", "npx", "npy", "nzc", "n_bins", "row_stride",
-        "plane_stride", "smem_bytes", "spread_threads", "gather_threads", "spread_batch")]
+        "nx", "ny", "nz", "nodes", "tx", "ty", "zw", "npx", "npy", "nzc", "nzt", "gather_nzt", "n_bins", "row_stride",
+        "plane_stride", "smem_bytes", "spread_threads", "gather_threads", "spread_batch", "spread_tiled")]
 
 
 class _SlabPeers(ctypes.Structure):
@@ -266,7 +266,8 @@ def slab_select_points(positions, r2u, ns, nodes: int, slab):
 #: enough to pay for the sort; "off": always the direct kernels; "on": tiled whenever covered
 TILE_MODE = os.environ.get("TPME_TILES", "auto")
 TILE_MIN_POINTS = int(os.environ.get("TPME_TILE_MIN_POINTS", "65536"))
-#: "auto" | "on" | "off": spread through the shared-memory pencils, or the direct kernel over the sorted atoms
+#: "auto" | "on" | "off": spread through the shared-memory pencils or the direct kernel (part of the tile
+#: plan: the library reads TPME_TILE_SPREAD itself; this copy only keys the plan cache)
 TILE_SPREAD = os.environ.get("TPME_TILE_SPREAD", "auto")
 
 
@@ -291,13 +292,9 @@ class TileSort:
         key_rank = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
         self.rec = torch.empty((max(n, 1), 4), dtype=positions.dtype, device=dev)
         self.idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        # Where the spread goes.  Measured on B200 (profiles/r02_tiles.md): the shared-memory pencils win
-        # in fp64 and whenever a mesh cell holds >= ~0.1 atoms (c3: 52 -> 46 us, c5: 38 -> 28 us); for
-        # sparse fp32 meshes (c4: 0.06 atoms per cell) the L2 reduction atomics of the direct kernel are
-        # faster (95 vs 118 us), so the spread stays there and only the gathers use the tiles.
-        density = n / float(plan.nx * plan.ny * plan.nz)
-        self.spread_tiled = (positions.dtype == torch.float64 or density >= 0.09) \
-            if TILE_SPREAD == "auto" else TILE_SPREAD == "on"
+        # where the spread goes is part of the plan (tpme_tile_plan_make: tiled in fp64 and for dense
+        # meshes, the direct kernel otherwise; TPME_TILE_SPREAD = on | off overrides)
+        self.spread_tiled = bool(plan.spread_tiled)
         self.count = None
         with _on(positions, "positions"):
             _check(lib.tpme_tile_sort(_dtype_id(positions), ctypes.byref(plan), _dev(positions, "positions"), n,
@@ -316,11 +313,15 @@ def tile_plan(dtype, ns, nodes: int, method: int, n_points: int):
     if TILE_MODE == "off" or n_points <= 0 or (TILE_MODE != "on" and n_points < TILE_MIN_POINTS):
         return None
     # the plan depends on the point count only through the block sizes: bucket it
-    key = (dtype, tuple(int(v) for v in ns), int(nodes), int(method), int(n_points).bit_length())
+    key = (dtype, tuple(int(v) for v in ns), int(nodes), int(method), int(n_points).bit_length(), TILE_SPREAD)
     if key in _tile_plans:
         return _tile_plans[key]
     lib = load()
     plan = _TilePlan()
+    if TILE_SPREAD in ("on", "off"):
+        os.environ["TPME_TILE_SPREAD"] = TILE_SPREAD      # the library reads the switch when it makes the plan
+    else:
+        os.environ.pop("TPME_TILE_SPREAD", None)
     rc = lib.tpme_tile_plan_make(0 if dtype == torch.float32 else 1, int(ns[0]), int(ns[1]), int(ns[2]),
                                  int(nodes), int(method), int(n_points), ctypes.byref(plan))
     if rc not in (0, 3):
