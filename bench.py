@@ -663,8 +663,8 @@ def run_b200(args, wl_name):
             def e2e_nl_step():
                 c_pos = host["positions"].to(device, non_blocking=True).requires_grad_(True)
                 c_q = host["charges"].to(device, non_blocking=True)
-                nl_idx, _, nl_shifts = neighbor_list(c_pos.detach(), cell, CUTOFF)
-                nl_d = distances_from(c_pos, cell, nl_idx, nl_shifts)
+                nl_idx, nl_d0, nl_shifts = neighbor_list(c_pos.detach(), cell, CUTOFF, index_dtype=torch.int32)
+                nl_d = distances_from(c_pos, cell, nl_idx, nl_shifts, known_distances=nl_d0)
                 V = calc(c_q, cell, c_pos, nl_idx, nl_d)
                 energy = (V * c_q).sum()
                 (g_pos,) = torch.autograd.grad(energy, (c_pos,))
@@ -672,13 +672,35 @@ def run_b200(args, wl_name):
                 h_energy.copy_(energy.detach(), non_blocking=True)
 
             k_nl = max(3, min(args.steps, 10))
-            nl_ms = timer(e2e_nl_step, k_nl, 2) / k_nl
+            nl_eager_ms = timer(e2e_nl_step, k_nl, 2) / k_nl
+            # the same step as one CUDA graph: fixed-capacity list, the pair count never leaves the device
+            pstep = tp.GraphedPositionsStep(calc, q, cell, inputs["positions"], cutoff=CUTOFF, host_io=True, warmup=1)
+            nl_ms = timer(pstep.replay, args.steps, warm) / args.steps
+            torch.cuda.synchronize()
+            # its forces are the complete ones (mesh + real space): check them against the same step launched
+            # eagerly over the exact-size list
+            p_ = inputs["positions"].detach()
+            i_full, _, s_full = neighbor_list(p_, cell, CUTOFF)
+            pr = p_.clone().requires_grad_(True)
+            Vr = calc(q, cell, pr, i_full, distances_from(pr, cell, i_full, s_full))
+            (gr,) = torch.autograd.grad(Vr, pr, grad_outputs=q)
+            got = pstep.host["grad_positions"].to(device)
+            nl_check = {"forces_vs_eager_exact_list": float((got - gr).abs().max() / gr.abs().max()),
+                        "pairs": int(pstep.host["n_pairs"]), "pairs_generator": int(inputs["neighbor_indices"].shape[0]),
+                        "capacity": pstep.capacity, "overflowed": pstep.overflowed()}
+            del i_full, s_full, pr, Vr, gr, got
             e2e_nl = {"ms_per_step": nl_ms, "value": world * n_atoms / (nl_ms * 1e-3), "unit": "atom-steps/s",
                       "h2d_bytes_per_step": nbytes(host["positions"]) + nbytes(host["charges"]),
-                      "d2h_bytes_per_step": d2h,
-                      "path": "positions + charges H2D only; torchpme_b200.neighbors.neighbor_list builds the half list "
-                              "on the device every step (cell-list kernels, build time included, one host sync for "
-                              "the pair count), distances recomputed differentiably, forces incl. the real-space part"}
+                      "d2h_bytes_per_step": d2h + 8,
+                      "eager_ms_per_step": nl_eager_ms,
+                      "check": nl_check,
+                      "path": "positions + charges H2D only; GraphedPositionsStep(host_io=True): ONE CUDA graph that "
+                              "copies positions / charges in, builds the half neighbor list on the device "
+                              "(neighbors.DeviceNeighborList: counting sort + 2-pass cell-list search, fixed-capacity "
+                              "buffers, pair count stays on the device), ties the distances to the positions "
+                              "(distances_from), runs the calculator forward + backward and copies energy + complete "
+                              "forces (mesh + real space) out; eager_ms_per_step is the same step launched from Python "
+                              "with neighbor_list() (one host sync for the pair count)"}
         except Exception as exc:
             e2e_nl = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     clocks = sampler.stop() if rank == 0 else None

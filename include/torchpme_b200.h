@@ -111,7 +111,8 @@ int tpme_slab_select_points(int dtype, const void* positions, int64_t n_points,
  * the mesh / stencil is not covered: use the direct calls); tpme_tile_sort bins the points once per set
  * of positions; the spread accumulates a pencil of the mesh in shared memory and flushes it with
  * cp.reduce.async.bulk, the gather stages the pencil with cp.async.bulk behind an mbarrier.
- * Workspace (device, caller-allocated): bin_count (n_bins) int32, bin_start (n_bins + 1) int32,
+ * Workspace (device, caller-allocated): bin_count (tpme_tile_bin_count_ints(plan) int32, 8-byte aligned:
+ * the counters followed by the scratch of the single-pass scan), bin_start (n_bins + 1) int32,
  * key_rank (2 N) int32 8-byte aligned, sorted_rec (4 N) reals 16-byte aligned, sorted_idx (N) int32. */
 typedef struct tpme_tile_plan {
   int nx, ny, nz, nodes;
@@ -128,6 +129,7 @@ typedef struct tpme_tile_plan {
 } tpme_tile_plan;
 int tpme_tile_plan_make(int dtype, int nx, int ny, int nz, int nodes, int method, int64_t n_points,
                         tpme_tile_plan* plan_host);
+int64_t tpme_tile_bin_count_ints(const tpme_tile_plan* plan_host);
 int tpme_tile_sort(int dtype, const tpme_tile_plan* plan_host, const void* positions, int64_t n_points,
                    const double* r2u_host, int* bin_count, int* bin_start, int* key_rank,
                    void* sorted_rec, int* sorted_idx, void* stream);
@@ -267,7 +269,10 @@ int tpme_multimem_allreduce(int dtype, void* multicast_ptr, int n_ranks, int ran
  * kind: 0 = per-pair values given in `pair_values`; 1 = Coulomb; 2 = inverse power law.
  *   out[i, c] += 1/2 sum_{p: i_p = i} q[j_p, c] v(d_p)  (+ the mirrored term for half lists)
  * `out` must be zeroed by the caller.  `pair_mask` (uint8, may be NULL) zeroes pairs.
- * `exclusion_radius` <= 0 means "not set". */
+ * `exclusion_radius` <= 0 means "not set".  `n_pairs_dev` (device, may be NULL): the number of valid
+ * pairs when the list sits in a buffer of capacity `n_pairs` (a neighbor list built on the device without
+ * a host synchronisation, tpme_nl_fill): pairs p >= *n_pairs_dev are skipped and their grad_pairs entries
+ * are left untouched. */
 typedef struct tpme_pair_potential {
   int kind;
   int exponent;
@@ -280,8 +285,8 @@ typedef struct tpme_pair_potential {
 
 int tpme_pair_forward(int dtype, const void* charges, const void* neighbor_indices,
                       int index_is_int64, const void* distances, const void* pair_values,
-                      const uint8_t* pair_mask, int64_t n_pairs, int64_t n_atoms,
-                      int n_channels, int full_neighbor_list,
+                      const uint8_t* pair_mask, int64_t n_pairs, const int64_t* n_pairs_dev,
+                      int64_t n_atoms, int n_channels, int full_neighbor_list,
                       const tpme_pair_potential* potential_host, void* out, void* stream);
 /* backward of the above for L with dL/dout = grad_out:
  *   grad_charges (N,C), accumulated, may be NULL
@@ -289,22 +294,27 @@ int tpme_pair_forward(int dtype, const void* charges, const void* neighbor_indic
 int tpme_pair_backward(int dtype, const void* charges, const void* neighbor_indices,
                        int index_is_int64, const void* distances, const void* pair_values,
                        const uint8_t* pair_mask, const void* grad_out, int64_t n_pairs,
-                       int64_t n_atoms, int n_channels, int full_neighbor_list,
+                       const int64_t* n_pairs_dev, int64_t n_atoms, int n_channels, int full_neighbor_list,
                        const tpme_pair_potential* potential_host, void* grad_charges,
                        void* grad_pairs, void* stream);
 
-/* ---- EXPERIMENTAL: neighbor list on the GPU -------------------
+/* ---- neighbor list on the GPU -----------------------------------
  * The reference takes the neighbor list from the external `vesin` package (tests/helpers.py:240-275,
- * examples/basic-usage.py:166-169).  Cell-list search in two passes over atoms that the caller has
- * wrapped into the cell, binned (slabs between lattice planes, `n_bins[a]` per direction) and sorted
- * by bin:  wrapped (N,3) reals, wrap_shift (N,3) int32 (wrapped = r - wrap_shift . cell),
- * atom_bins (N,3) int32, order (N) int32 (sorted slot -> atom), bin_start (prod(n_bins)+1) int32.
- *   tpme_neighbor_count  counts[slot] = neighbors of the atom in sorted slot `slot`
- *   tpme_neighbor_fill   with the exclusive scan `offsets` of the counts: indices (P,2) int64,
- *                        squared distances (P), integer image shifts (P,3) w.r.t. the original positions
- * A pair (i, j, S) is the image r_j + S . cell seen from r_i; half lists keep i < j (any S) and
- * self images with S lexicographically positive.  Not yet validated on a GPU; the search loop
- * itself (csrc/neighbors_core.h) is validated on the CPU by tests/test_neighbors.py. */
+ * examples/basic-usage.py:166-169).  Cell list: atoms are wrapped into the cell along the periodic
+ * directions, binned into slabs between lattice planes (`n_bins[a]` per direction; 1 for non-periodic
+ * directions) and sorted by bin; one thread per sorted atom then walks `reach[a]` bins on either side.
+ * A pair (i, j, S) is the image r_j + S . cell seen from r_i; half lists keep i < j (any S) and self
+ * images with S lexicographically positive; full lists hold both directions.
+ *   tpme_nl_sort   wrap + bin + counting sort of the atoms into sorted_rec / sorted_shift / bin_start
+ *   tpme_nl_pairs  the search: *n_pairs_dev = number of pairs (stays on the device); with `indices` != NULL
+ *                  also indices (capacity,2) int32 / int64, distances (capacity) reals, shifts (capacity,3)
+ *                  int32 (w.r.t. the positions as given, not the wrapped ones).  Pairs beyond `capacity`
+ *                  are dropped -- compare *n_pairs_dev with the capacity.  The pairs of one atom are
+ *                  contiguous; the order of the atoms' runs depends on the scheduling of the CTAs.
+ * Workspace (device, caller-allocated, 16-byte aligned): scratch (tpme_nl_scratch_ints int32), bin_start
+ * (prod(n_bins) + 1) int32, sorted_rec (N records of 16 bytes in fp32 / 32 bytes in fp64),
+ * sorted_shift (N,4) int32.
+ * The per-atom code (csrc/neighbors_core.h) also runs on the CPU in tests/test_neighbors.py. */
 typedef struct tpme_neighbor_search {
   double cell[9];    /* host, row-major, rows = lattice vectors */
   int n_bins[3];
@@ -313,13 +323,25 @@ typedef struct tpme_neighbor_search {
   int full_list;
   double cutoff;
 } tpme_neighbor_search;
-int tpme_neighbor_count(int dtype, const void* wrapped, const int* wrap_shift, const int* atom_bins,
-                        const int* order, const int* bin_start, int64_t n_atoms,
-                        const tpme_neighbor_search* search_host, int* counts, void* stream);
-int tpme_neighbor_fill(int dtype, const void* wrapped, const int* wrap_shift, const int* atom_bins,
-                       const int* order, const int* bin_start, int64_t n_atoms,
-                       const tpme_neighbor_search* search_host, const int64_t* offsets,
-                       int64_t* indices, void* distances_sq, int* shifts, void* stream);
+int64_t tpme_nl_scratch_ints(int64_t n_atoms, const tpme_neighbor_search* search_host);
+int tpme_nl_sort(int dtype, const void* positions, int64_t n_atoms, const tpme_neighbor_search* search_host,
+                 int* scratch, int* bin_start, void* sorted_rec, int* sorted_shift, void* stream);
+int tpme_nl_pairs(int dtype, const void* sorted_rec, const int* sorted_shift, const int* bin_start,
+                  int64_t n_atoms, const tpme_neighbor_search* search_host, int64_t capacity,
+                  int index_is_int64, void* indices, void* distances, int* shifts, int64_t* n_pairs_dev,
+                  void* stream);
+/* d_p = |r_j + S_p . cell - r_i| for a pair list with image shifts, and its vector-Jacobian product:
+ * grad_positions (N,4) -- padded to 4 reals per atom so that the three components travel as one 16-byte
+ * vector reduction, 16-byte aligned -- accumulated, grad_cell (9 reals, accumulated, may be NULL).  What the reference's
+ * users get from vesin's torch front end (examples/basic-usage.py:161-169) so that forces
+ * reach the positions through neighbor_distances.  `n_pairs_dev` as for tpme_pair_forward. */
+int tpme_pair_distances(int dtype, const void* positions, const double* cell_host,
+                        const void* neighbor_indices, int index_is_int64, const int* shifts, int64_t n_pairs,
+                        const int64_t* n_pairs_dev, void* distances, void* stream);
+int tpme_pair_distances_backward(int dtype, const void* positions, const double* cell_host,
+                                 const void* neighbor_indices, int index_is_int64, const int* shifts,
+                                 const void* grad_distances, int64_t n_pairs, const int64_t* n_pairs_dev,
+                                 void* grad_positions, void* grad_cell, void* stream);
 
 #ifdef __cplusplus
 }

@@ -107,5 +107,10 @@ def test_slab_and_peer_entry_points_validate_arguments_without_a_gpu():
     assert lib.tpme_peer_barrier(a, 0, 0, dummy, 1.0, dummy, None) != 0 and "rank layout" in err()
     # neighbor search parameters
     search = _native._NeighborSearch()
-    assert lib.tpme_neighbor_count(0, dummy, dummy, dummy, dummy, dummy, 4, ctypes.byref(search), dummy, None) != 0
+    assert lib.tpme_nl_sort(0, dummy, 4, ctypes.byref(search), dummy, dummy, dummy, dummy, None) != 0
     assert "cutoff" in err()
+    search.cutoff = 1.0
+    for a in range(3):
+        search.n_bins[a] = 1
+    assert lib.tpme_nl_pairs(0, dummy, dummy, dummy, 4, ctypes.byref(search), 8, 0, dummy, dummy, dummy, dummy, None) != 0
+    assert "singular" in err()

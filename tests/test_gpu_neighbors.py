@@ -1,6 +1,6 @@
 """
-Neighbor list built on the GPU (torchpme_b200.neighbors: cell-list kernels tpme_neighbor_count /
-tpme_neighbor_fill) against the brute-force oracle (oracle.neighbor_list, the stand-in for the
+Neighbor list built on the GPU (torchpme_b200.neighbors: cell-list kernels tpme_nl_count /
+tpme_nl_fill) against the brute-force oracle (oracle.neighbor_list, the stand-in for the
 reference's external `vesin` dependency, tests/helpers.py:240-275): the SAME set of (i, j, image)
 pairs with the same distances, for cubic / triclinic / smaller-than-cutoff cells, half and full lists,
 fp32 and fp64, 2-D periodic and open systems; at 1 M atoms against the pair list of the synthetic
@@ -121,3 +121,98 @@ def test_one_million_atoms_against_the_generator(dtype):
     deg = torch.zeros(n, device="cuda").index_add_(0, idx[sure].reshape(-1), ones(2 * int(sure.sum())))
     deg_ref = torch.zeros(n, device="cuda").index_add_(0, idx_ref[sure_ref].reshape(-1), ones(2 * int(sure_ref.sum())))
     assert torch.equal(deg, deg_ref)
+
+
+def test_int32_indices_and_known_distances():
+    from torchpme_b200.neighbors import distances_from, neighbor_list
+
+    pos, q, cell, _, _ = rocksalt(6, dtype=torch.float32, device="cuda", cutoff=5.0)
+    idx64, d64, s64 = neighbor_list(pos, cell, 4.5)
+    idx32, d32, s32 = neighbor_list(pos, cell, 4.5, index_dtype=torch.int32)
+    assert idx32.dtype == torch.int32 and idx64.dtype == torch.int64
+    # the order inside a bin depends on atomics: compare as sets
+    def key(i, s):
+        image = ((s[:, 0] + 1) * 9 + (s[:, 1] + 1) * 3 + (s[:, 2] + 1)).long()
+        return torch.sort((i[:, 0].long() * 4096 + i[:, 1].long()) * 27 + image).values
+
+    assert torch.equal(key(idx64, s64), key(idx32, s32))
+    p = pos.clone().requires_grad_(True)
+    a = distances_from(p, cell, idx32, s32, known_distances=d32)
+    b = distances_from(p, cell, idx32, s32)
+    assert rel_err(a.detach(), b.detach()) < 1e-6
+    (ga,) = torch.autograd.grad(a.square().sum(), p)
+    (gb,) = torch.autograd.grad(b.square().sum(), p)
+    assert rel_err(ga, gb) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("full", [False, True], ids=["half", "full"])
+def test_fixed_capacity_list_through_the_calculator(dtype, full):
+    """DeviceNeighborList (no host sync, padded buffers, pair count on the device): same potentials and
+    forces as the exact-size list, padding entries never touched, overflow detected"""
+    import torchpme_b200 as tp
+    from torchpme_b200.neighbors import DeviceNeighborList, distances_from, neighbor_list
+
+    pos, q, cell, _, _ = rocksalt(8, dtype=dtype, device="cuda", cutoff=5.0)
+    cutoff = 5.0
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=1.1).to("cuda"), mesh_spacing=float(cell[0, 0]) / 14,
+                            full_neighbor_list=full)
+
+    def step(idx, shifts, known):
+        p = pos.clone().requires_grad_(True)
+        d = distances_from(p, cell, idx, shifts, known_distances=known)
+        V = calc(q, cell, p, idx, d)
+        (g,) = torch.autograd.grad(V, p, grad_outputs=q)
+        return V.detach(), g
+
+    idx, d, s = neighbor_list(pos, cell, cutoff, full_neighbor_list=full)
+    V_ref, F_ref = step(idx, s, None)
+    nl = DeviceNeighborList(pos.shape[0], cell, cutoff, capacity=idx.shape[0] + 777, dtype=dtype,
+                            full_neighbor_list=full)
+    i2, d2, s2 = nl.build(pos)
+    assert int(nl.n_pairs) == idx.shape[0] and not nl.overflowed()
+    assert i2.shape[0] == idx.shape[0] + 777 and bool((i2[idx.shape[0]:] == 0).all())
+    V, F = step(i2, s2, d2)
+    tol = 1e-11 if dtype == torch.float64 else 2e-5
+    assert rel_err(V, V_ref) < tol and rel_err(F, F_ref) < tol
+    # against the oracle's pair list too (independent of the device list)
+    o_idx, o_d, o_s = oracle.neighbor_list(pos.double().cpu().numpy(), cell.double().cpu().numpy(), cutoff, full=full)
+    V_o, F_o = step(torch.tensor(o_idx, device="cuda"), torch.tensor(o_s, device="cuda", dtype=torch.int32), None)
+    assert rel_err(V, V_o) < tol and rel_err(F, F_o) < tol
+    small = DeviceNeighborList(pos.shape[0], cell, cutoff, capacity=idx.shape[0] // 2, dtype=dtype, full_neighbor_list=full)
+    small.build(pos)
+    assert small.overflowed() and int(small.n_pairs) == idx.shape[0]
+
+
+def test_graphed_positions_step_matches_the_list_based_step():
+    """positions-only step captured as one CUDA graph (list build + calculator + backward), with and without
+    host I/O, replayed for moved atoms"""
+    import torchpme_b200 as tp
+    from torchpme_b200.neighbors import distances_from, neighbor_list
+
+    pos, q, cell, _, _ = rocksalt(10, dtype=torch.float64, device="cuda", cutoff=5.0)
+    calc = tp.P3MCalculator(tp.CoulombPotential(smearing=1.2).to("cuda"), mesh_spacing=float(cell[0, 0]) / 14)
+
+    def eager(positions):
+        idx, d, s = neighbor_list(positions, cell, 5.0)
+        p = positions.clone().requires_grad_(True)
+        V = calc(q, cell, p, idx, distances_from(p, cell, idx, s))
+        E = (V * q).sum()
+        (g,) = torch.autograd.grad(E, p)
+        return E.detach(), g
+
+    for host_io in (False, True):
+        step = tp.GraphedPositionsStep(calc, q, cell, pos, cutoff=5.0, host_io=host_io)
+        gen = torch.Generator("cuda").manual_seed(5)
+        for _ in range(3):
+            moved = pos + 0.2 * torch.randn(pos.shape, dtype=pos.dtype, device="cuda", generator=gen)
+            if host_io:
+                step.host["positions"].copy_(moved)
+                step.replay()
+                torch.cuda.synchronize()
+                E, g = step.host["energy"].cuda(), step.host["grad_positions"].cuda()
+            else:
+                E, g = step(positions=moved)
+            assert not step.overflowed()
+            E_ref, g_ref = eager(moved)
+            assert rel_err(E, E_ref) < 1e-11 and rel_err(g, g_ref) < 1e-10

@@ -1,8 +1,8 @@
 """
-EXPERIMENTAL neighbor list: the search loop of ``torch-pme_b200/csrc/neighbors_core.h`` (what each
-CUDA thread executes) is compiled for the host (tests/native/nl_host.cpp, g++) and driven through the
-package's own Python plumbing, then compared with the brute-force oracle on periodic / non-periodic,
-cubic / triclinic, large / smaller-than-cutoff cells, half and full lists, fp64 and fp32.
+Neighbor list: the per-atom code of ``torch-pme_b200/csrc/neighbors_core.h`` (wrap + bin, search loop:
+what each CUDA thread executes) is compiled for the host (tests/native/nl_host.cpp, g++) and driven
+through the package's own layout logic, then compared with the brute-force oracle on periodic /
+non-periodic, cubic / triclinic, large / smaller-than-cutoff cells, half and full lists, fp64 and fp32.
 """
 import ctypes
 import os
@@ -20,28 +20,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.fixture(scope="module")
 def host_search(tmp_path_factory):
+    """the per-atom code of csrc/neighbors_core.h built for the host; passed to neighbor_list(_host_library=...)"""
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     so = str(tmp_path_factory.mktemp("nl") / "nl_host.so")
     subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
                     os.path.join(HERE, "native", "nl_host.cpp")], check=True)
-    lib = ctypes.CDLL(so)
-    vp = ctypes.c_void_p
-
-    def run(dtype_id, wrapped, wrap_shift, atom_bins, order, bin_start, n, search, offsets=None, outputs=None):
-        ptr = lambda t: vp(t.data_ptr())  # noqa: E731
-        common = (dtype_id, ptr(wrapped), ptr(wrap_shift), ptr(atom_bins), ptr(order), ptr(bin_start),
-                  ctypes.c_int64(n), search.cell, search.n_bins, search.reach, search.periodic,
-                  ctypes.c_int(search.full_list), ctypes.c_double(search.cutoff))
-        if offsets is None:
-            counts = torch.empty(n, dtype=torch.int32)
-            assert lib.nl_host_count(*common, ptr(counts)) == 0
-            return counts
-        indices, dist_sq, shifts = outputs
-        assert lib.nl_host_fill(*common, ptr(offsets), ptr(indices), ptr(dist_sq), ptr(shifts)) == 0
-        return None
-
-    return run
+    return ctypes.CDLL(so)
 
 
 def _canonical(idx, d, shifts):
@@ -76,7 +61,7 @@ def test_search_loop_matches_bruteforce_oracle(host_search, name, full, dtype):
     cutoff = 3.7
     ref_idx, ref_d, ref_s = oracle.neighbor_list(pos, cell, cutoff, full=full)
     idx, d, s = neighbor_list(torch.tensor(pos, dtype=dtype), torch.tensor(cell, dtype=dtype), cutoff,
-                              full_neighbor_list=full, _search=host_search)
+                              full_neighbor_list=full, _host_library=host_search)
     assert idx.dtype == torch.int64 and s.dtype == torch.int32 and d.dtype == dtype
     if full:
         # both directions present: compare as multisets of directed pairs
@@ -101,13 +86,13 @@ def test_non_periodic_all_pairs(host_search):
     rng = np.random.default_rng(2)
     pos = torch.tensor(rng.random((9, 3)) * 4.0)
     cell = torch.eye(3, dtype=torch.float64)
-    idx, d, s = neighbor_list(pos, cell, 100.0, periodic=(False, False, False), _search=host_search)
+    idx, d, s = neighbor_list(pos, cell, 100.0, periodic=(False, False, False), _host_library=host_search)
     assert idx.shape[0] == 9 * 8 // 2 and int(s.abs().sum()) == 0
     assert bool((idx[:, 0] < idx[:, 1]).all())
     np.testing.assert_allclose(d.numpy(), distances_from(pos, cell, idx, s).numpy(), rtol=1e-13)
     # slab geometry: periodic in x and y only
     cell = torch.tensor([[3.0, 0, 0], [0, 3.5, 0], [0, 0, 50.0]], dtype=torch.float64)
-    idx, d, s = neighbor_list(pos, cell, 2.5, periodic=(True, True, False), _search=host_search)
+    idx, d, s = neighbor_list(pos, cell, 2.5, periodic=(True, True, False), _host_library=host_search)
     assert int(s[:, 2].abs().sum()) == 0 and idx.shape[0] > 0
     np.testing.assert_allclose(d.numpy(), distances_from(pos, cell, idx, s).numpy(), rtol=1e-12)
     assert float(d.max()) < 2.5

@@ -134,9 +134,10 @@ template <typename T, typename I, bool HALF>
 __global__ void __launch_bounds__(256)
 pair_forward_coulomb_kernel(const T* __restrict__ charges, const I* __restrict__ idx,
                             const T* __restrict__ dist, const uint8_t* __restrict__ mask,
-                            int64_t n_pairs, T a, T half_pref, T* __restrict__ out) {
+                            int64_t n_pairs, const int64_t* __restrict__ n_dev, T a, T half_pref,
+                            T* __restrict__ out) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
+  if (p >= n_pairs || (n_dev != nullptr && p >= *n_dev)) return;
   if (mask != nullptr && mask[p] == 0) return;
   int64_t i, j;
   IndexPair<I>::load(idx, p, i, j);
@@ -150,10 +151,11 @@ template <typename T, typename I, bool HALF>
 __global__ void __launch_bounds__(256)
 pair_backward_coulomb_kernel(const T* __restrict__ charges, const I* __restrict__ idx,
                              const T* __restrict__ dist, const uint8_t* __restrict__ mask,
-                             const T* __restrict__ grad_out, int64_t n_pairs, T a, T half_pref,
+                             const T* __restrict__ grad_out, int64_t n_pairs,
+                             const int64_t* __restrict__ n_dev, T a, T half_pref,
                              T* __restrict__ grad_charges, T* __restrict__ grad_pairs) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
+  if (p >= n_pairs || (n_dev != nullptr && p >= *n_dev)) return;
   if (mask != nullptr && mask[p] == 0) {
     if (grad_pairs) grad_pairs[p] = T(0);
     return;
@@ -177,10 +179,11 @@ template <typename T, typename I>
 __global__ void __launch_bounds__(256)
 pair_forward_kernel(const T* __restrict__ charges, const I* __restrict__ idx,
                     const T* __restrict__ dist, const T* __restrict__ pair_values,
-                    const uint8_t* __restrict__ mask, int64_t n_pairs, int n_channels,
+                    const uint8_t* __restrict__ mask, int64_t n_pairs,
+                    const int64_t* __restrict__ n_dev, int n_channels,
                     int full_list, PairPot<T> pp, T* __restrict__ out) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
+  if (p >= n_pairs || (n_dev != nullptr && p >= *n_dev)) return;
   if (mask != nullptr && mask[p] == 0) return;
   const int64_t i = (int64_t)idx[2 * p], j = (int64_t)idx[2 * p + 1];
   T v, dv;
@@ -198,10 +201,10 @@ __global__ void __launch_bounds__(256)
 pair_backward_kernel(const T* __restrict__ charges, const I* __restrict__ idx,
                      const T* __restrict__ dist, const T* __restrict__ pair_values,
                      const uint8_t* __restrict__ mask, const T* __restrict__ grad_out,
-                     int64_t n_pairs, int n_channels, int full_list, PairPot<T> pp,
-                     T* __restrict__ grad_charges, T* __restrict__ grad_pairs) {
+                     int64_t n_pairs, const int64_t* __restrict__ n_dev, int n_channels, int full_list,
+                     PairPot<T> pp, T* __restrict__ grad_charges, T* __restrict__ grad_pairs) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
+  if (p >= n_pairs || (n_dev != nullptr && p >= *n_dev)) return;
   if (mask != nullptr && mask[p] == 0) {
     if (grad_pairs) grad_pairs[p] = T(0);
     return;
@@ -265,7 +268,7 @@ using namespace tpme;
 extern "C" int tpme_pair_forward(int dtype, const void* charges, const void* neighbor_indices,
                                  int index_is_int64, const void* distances,
                                  const void* pair_values, const uint8_t* pair_mask,
-                                 int64_t n_pairs, int64_t n_atoms, int n_channels,
+                                 int64_t n_pairs, const int64_t* n_pairs_dev, int64_t n_atoms, int n_channels,
                                  int full_neighbor_list, const tpme_pair_potential* pot,
                                  void* out, void* stream) {
   (void)n_atoms;
@@ -278,7 +281,7 @@ extern "C" int tpme_pair_forward(int dtype, const void* charges, const void* nei
     const double a = 1.0 / (pot->smearing * sqrt(2.0)), hp = 0.5 * pot->prefactor;
 #define GOC(T, I, H)                                                                                  \
   pair_forward_coulomb_kernel<T, I, H><<<grid, 256, 0, s>>>((const T*)charges, (const I*)neighbor_indices, \
-      (const T*)distances, pair_mask, n_pairs, (T)a, (T)hp, (T*)out)
+      (const T*)distances, pair_mask, n_pairs, n_pairs_dev, (T)a, (T)hp, (T*)out)
 #define GOCI(T, I) do { if (full_neighbor_list) GOC(T, I, false); else GOC(T, I, true); } while (0)
     if (dtype == 0) { if (index_is_int64) GOCI(float, int64_t); else GOCI(float, int32_t); }
     else            { if (index_is_int64) GOCI(double, int64_t); else GOCI(double, int32_t); }
@@ -289,7 +292,7 @@ extern "C" int tpme_pair_forward(int dtype, const void* charges, const void* nei
   }
 #define GO(T, I)                                                                              \
   pair_forward_kernel<T, I><<<grid, 256, 0, s>>>((const T*)charges, (const I*)neighbor_indices, \
-      (const T*)distances, (const T*)pair_values, pair_mask, n_pairs, n_channels,             \
+      (const T*)distances, (const T*)pair_values, pair_mask, n_pairs, n_pairs_dev, n_channels, \
       full_neighbor_list, make_pair_pot<T>(pot), (T*)out)
   if (dtype == 0) { if (index_is_int64) GO(float, int64_t); else GO(float, int32_t); }
   else            { if (index_is_int64) GO(double, int64_t); else GO(double, int32_t); }
@@ -301,7 +304,8 @@ extern "C" int tpme_pair_forward(int dtype, const void* charges, const void* nei
 extern "C" int tpme_pair_backward(int dtype, const void* charges, const void* neighbor_indices,
                                   int index_is_int64, const void* distances,
                                   const void* pair_values, const uint8_t* pair_mask,
-                                  const void* grad_out, int64_t n_pairs, int64_t n_atoms,
+                                  const void* grad_out, int64_t n_pairs, const int64_t* n_pairs_dev,
+                                  int64_t n_atoms,
                                   int n_channels, int full_neighbor_list,
                                   const tpme_pair_potential* pot, void* grad_charges,
                                   void* grad_pairs, void* stream) {
@@ -315,7 +319,7 @@ extern "C" int tpme_pair_backward(int dtype, const void* charges, const void* ne
     const double a = 1.0 / (pot->smearing * sqrt(2.0)), hp = 0.5 * pot->prefactor;
 #define GOC(T, I, H)                                                                                   \
   pair_backward_coulomb_kernel<T, I, H><<<grid, 256, 0, s>>>((const T*)charges, (const I*)neighbor_indices, \
-      (const T*)distances, pair_mask, (const T*)grad_out, n_pairs, (T)a, (T)hp, (T*)grad_charges,      \
+      (const T*)distances, pair_mask, (const T*)grad_out, n_pairs, n_pairs_dev, (T)a, (T)hp, (T*)grad_charges, \
       (T*)grad_pairs)
 #define GOCI(T, I) do { if (full_neighbor_list) GOC(T, I, false); else GOC(T, I, true); } while (0)
     if (dtype == 0) { if (index_is_int64) GOCI(float, int64_t); else GOCI(float, int32_t); }
@@ -328,7 +332,7 @@ extern "C" int tpme_pair_backward(int dtype, const void* charges, const void* ne
 #define GO(T, I)                                                                               \
   pair_backward_kernel<T, I><<<grid, 256, 0, s>>>((const T*)charges, (const I*)neighbor_indices, \
       (const T*)distances, (const T*)pair_values, pair_mask, (const T*)grad_out, n_pairs,       \
-      n_channels, full_neighbor_list, make_pair_pot<T>(pot), (T*)grad_charges, (T*)grad_pairs)
+      n_pairs_dev, n_channels, full_neighbor_list, make_pair_pot<T>(pot), (T*)grad_charges, (T*)grad_pairs)
   if (dtype == 0) { if (index_is_int64) GO(float, int64_t); else GO(float, int32_t); }
   else            { if (index_is_int64) GO(double, int64_t); else GO(double, int32_t); }
 #undef GO

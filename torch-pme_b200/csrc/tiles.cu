@@ -26,6 +26,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "scan.cuh"
 #include "stencil_point.cuh"
 #include "../../include/torchpme_b200.h"
 
@@ -137,76 +138,6 @@ tile_count_kernel(const T* __restrict__ positions, int64_t n_points, Mat3<T> r2u
   point_first<T>(positions + 3 * i, r2u, dims, g.nodes, first, x);
   const int key = bin_of(g, first);
   key_rank[i] = make_int2(key, atomicAdd(counts + key, 1));
-}
-
-// exclusive scan of the n bin counters by ONE CTA (bin tables are small: 4 k .. a few 100 k entries):
-// blocks of 32 x 1024 counters are loaded coalesced (thread t holds elements r * 1024 + t of the block,
-// r = 0..31), scanned along t with warp shuffles + one shared-memory pass over the 32 x 32 warp totals,
-// and chained through a running carry.
-__global__ void __launch_bounds__(1024) tile_scan_kernel(const int* __restrict__ counts, int* __restrict__ start, int n) {
-  constexpr int R = 32;
-  __shared__ int warp_tot[R][33];    // [row][warp] inclusive totals of the warps of one row
-  __shared__ int row_base[R + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int carry = 0;
-  for (int block0 = 0; block0 < n; block0 += R * 1024) {
-    int v[R];
-    const int rows_used = min(R, (n - block0 + 1023) / 1024);   // small tables: fewer rows (block-uniform)
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int k = block0 + r * 1024 + (int)threadIdx.x;
-      v[r] = (r < rows_used && k < n) ? counts[k] : 0;
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {       // inclusive scan inside every warp, for all rows
-      if (r >= rows_used) { if (lane == 31) warp_tot[r][warp] = 0; continue; }
-      int x = v[r];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, off);
-        if (lane >= off) x += y;
-      }
-      v[r] = x;
-      if (lane == 31) warp_tot[r][warp] = x;
-    }
-    __syncthreads();
-    {   // warp w scans the 32 warp totals of row w; its last lane has the row total
-      int x = warp_tot[warp][lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, off);
-        if (lane >= off) x += y;
-      }
-      warp_tot[warp][lane] = x;
-      if (lane == 31) row_base[warp + 1] = x;
-    }
-    __syncthreads();
-    if (warp == 0) {   // exclusive scan of the row totals
-      int x = lane == 0 ? 0 : row_base[lane];
-      int t = x;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, t, off);
-        if (lane >= off) t += y;
-      }
-      const int last = row_base[32];
-      __syncwarp();
-      row_base[lane] = t;
-      if (lane == 31) row_base[32] = t + last;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int k = block0 + r * 1024 + (int)threadIdx.x;
-      if (k < n) {
-        const int incl = v[r] + (warp > 0 ? warp_tot[r][warp - 1] : 0) + row_base[r] + carry;
-        start[k] = incl - counts[k];
-      }
-    }
-    carry += row_base[32];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) start[n] = carry;
 }
 
 template <typename T>
@@ -772,6 +703,11 @@ extern "C" int tpme_tile_plan_make(int dtype, int nx, int ny, int nz, int nodes,
   return 0;
 }
 
+extern "C" int64_t tpme_tile_bin_count_ints(const tpme_tile_plan* plan) {
+  if (plan == nullptr || plan->n_bins <= 0) return 0;
+  return ((plan->n_bins + 1) & ~1) + 2 * scan_state_words(plan->n_bins);
+}
+
 extern "C" int tpme_tile_sort(int dtype, const tpme_tile_plan* plan, const void* positions, int64_t n_points,
                               const double* r2u_host, int* bin_count, int* bin_start,
                               int* key_rank, void* sorted_rec, int* sorted_idx, void* stream) {
@@ -781,7 +717,10 @@ extern "C" int tpme_tile_sort(int dtype, const tpme_tile_plan* plan, const void*
   TPME_REQUIRE(((uintptr_t)sorted_rec % 16) == 0 && ((uintptr_t)key_rank % 8) == 0, "workspace alignment");
   cudaStream_t s = (cudaStream_t)stream;
   const TileGeom g = geom_of(*plan, plan->nzt);
+  TPME_REQUIRE(((uintptr_t)bin_count % 8) == 0, "workspace alignment");
   TPME_CUDA_OK(cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)plan->n_bins, s));
+  // scratch of the scan: behind the counters, 8-byte aligned (tpme_tile_bin_count_ints)
+  void* scan_state = bin_count + ((plan->n_bins + 1) & ~1);
   const unsigned grid = (unsigned)((n_points + 255) / 256);
   if (n_points > 0) {
     if (dtype == 0)
@@ -791,7 +730,7 @@ extern "C" int tpme_tile_sort(int dtype, const tpme_tile_plan* plan, const void*
       tile_count_kernel<double><<<grid, 256, 0, s>>>((const double*)positions, n_points, load_mat3<double>(r2u_host),
                                                      make_dims<double>(g.nx, g.ny, g.nz), g, bin_count, (int2*)key_rank);
   }
-  tile_scan_kernel<<<1, 1024, 0, s>>>(bin_count, bin_start, plan->n_bins);
+  TPME_CUDA_OK(launch_exclusive_scan<int>(bin_count, bin_start, plan->n_bins, scan_state, s));
   if (n_points > 0) {
     if (dtype == 0)
       tile_fill_kernel<float><<<grid, 256, 0, s>>>((const float*)positions, n_points, load_mat3<float>(r2u_host),

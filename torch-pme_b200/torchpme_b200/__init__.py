@@ -14,7 +14,7 @@ Coulomb and inverse-power-law potentials, the mesh interpolator and k-space filt
 from . import calculators, graphs, lib, mesh, potentials, prefactors, tuning  # noqa: F401
 from ._native import NativeLibraryError, library_path  # noqa: F401
 from .calculators import Calculator, P3MCalculator, PMECalculator
-from .graphs import GraphedStep  # noqa: F401
+from .graphs import GraphedPositionsStep, GraphedStep  # noqa: F401
 from .mesh import set_nan_check  # noqa: F401
 from .potentials import (CombinedPotential, CoulombPotential, InversePowerLawPotential, Potential,
                          SplinePotential)

@@ -12,7 +12,9 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
+import weakref
 
+import numpy as np
 import torch
 
 _LIB_NAME = "libtorchpme_b200.so"
@@ -115,6 +117,7 @@ SIGNATURES = {
                               _i, _vp, ctypes.POINTER(_PointEpilogue), _vp], _i),
     "tpme_slab_select_points": ([_i, _vp, _i64, _dp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp], _i),
     "tpme_tile_plan_make": ([_i, _i, _i, _i, _i, _i, _i64, ctypes.POINTER(_TilePlan)], _i),
+    "tpme_tile_bin_count_ints": ([ctypes.POINTER(_TilePlan)], _i64),
     "tpme_tile_sort": ([_i, ctypes.POINTER(_TilePlan), _vp, _i64, _dp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "tpme_tile_spread": ([_i, ctypes.POINTER(_TilePlan), _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp], _i),
     "tpme_tile_gather": ([_i, ctypes.POINTER(_TilePlan), _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _dp, _i, _vp, _vp,
@@ -130,9 +133,10 @@ SIGNATURES = {
     "tpme_peer_buffer_close": ([_vp], _i),
     "tpme_peer_buffer_destroy": ([_vp], _i),
     "tpme_peer_barrier": ([ctypes.POINTER(_vp), _i, _i, _vp, ctypes.c_double, _vp, _vp], _i),
-    "tpme_neighbor_count": ([_i, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.POINTER(_NeighborSearch), _vp, _vp], _i),
-    "tpme_neighbor_fill": ([_i, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.POINTER(_NeighborSearch), _vp, _vp, _vp,
-                            _vp, _vp], _i),
+    "tpme_nl_scratch_ints": ([_i64, ctypes.POINTER(_NeighborSearch)], _i64),
+    "tpme_nl_sort": ([_i, _vp, _i64, ctypes.POINTER(_NeighborSearch), _vp, _vp, _vp, _vp, _vp], _i),
+    "tpme_nl_pairs": ([_i, _vp, _vp, _vp, _i64, ctypes.POINTER(_NeighborSearch), _i64, _i, _vp, _vp, _vp, _vp,
+                       _vp], _i),
     "tpme_multimem_allreduce": ([_i, _vp, _i, _i, _i64, _vp], _i),
     "tpme_peer_allreduce": ([_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _i64, _vp], _i),
     "tpme_fft_plan_create": ([ctypes.POINTER(_vp), _i, _i, _i, _i, _i], _i),
@@ -144,10 +148,12 @@ SIGNATURES = {
     "tpme_kfilter_apply": ([_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_Green), _vp, _vp], _i),
     "tpme_green_table": ([_i, _vp, _i, _i, _i, ctypes.POINTER(_Green), _vp], _i),
     "tpme_green_table_vjp": ([_i, _vp, _vp, _i, _i, _i, _i, ctypes.c_double, _vp, _vp], _i),
-    "tpme_pair_forward": ([_i, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _i, _i,
+    "tpme_pair_forward": ([_i, _vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i,
                            ctypes.POINTER(_PairPotential), _vp, _vp], _i),
-    "tpme_pair_backward": ([_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i,
+    "tpme_pair_backward": ([_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i,
                             ctypes.POINTER(_PairPotential), _vp, _vp, _vp], _i),
+    "tpme_pair_distances": ([_i, _vp, _dp, _vp, _i, _vp, _i64, _vp, _vp, _vp], _i),
+    "tpme_pair_distances_backward": ([_i, _vp, _dp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp], _i),
 }
 
 _lib = None
@@ -287,7 +293,7 @@ class TileSort:
         dev = positions.device
         self.plan, self.n_points, self.r2u, self.dtype = plan, n, r2u, positions.dtype
         self.positions = positions
-        counts = torch.empty(plan.n_bins, dtype=torch.int32, device=dev)
+        counts = torch.empty(int(lib.tpme_tile_bin_count_ints(ctypes.byref(plan))), dtype=torch.int32, device=dev)
         self.bin_start = torch.empty(plan.n_bins + 1, dtype=torch.int32, device=dev)
         key_rank = torch.empty((max(n, 1), 2), dtype=torch.int32, device=dev)
         self.rec = torch.empty((max(n, 1), 4), dtype=positions.dtype, device=dev)
@@ -776,6 +782,24 @@ def _index_args(idx):
     raise TypeError(f"neighbor_indices must be int32 or int64, got {idx.dtype}")
 
 
+#: number of valid pairs (0-dim int64 device tensor) of index buffers that hold a list built on the device
+#: without a host synchronisation (neighbors.DeviceNeighborList), keyed by the buffer's address
+_pair_counts: dict = {}
+
+
+def register_pair_count(indices: torch.Tensor, count: torch.Tensor) -> None:
+    """the pairs ``p >= count`` of ``indices`` (and of everything indexed like it) are padding"""
+    if count.dtype != torch.int64 or count.numel() != 1 or count.device != indices.device:
+        raise ValueError("`count` must be a one-element int64 tensor on the device of `indices`")
+    ref = weakref.ref(indices, lambda _, key=indices.data_ptr(): _pair_counts.pop(key, None))
+    _pair_counts[indices.data_ptr()] = (ref, count)
+
+
+def pair_count_of(indices: torch.Tensor):
+    hit = _pair_counts.get(indices.data_ptr())
+    return None if hit is None else hit[1]
+
+
 def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot: _PairPotential,
                  out=None):
     """accumulates into `out` (allocated and zeroed here when None)"""
@@ -787,7 +811,8 @@ def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot:
         _check(lib.tpme_pair_forward(_dtype_id(charges), _dev(charges, "charges"),
                                      _dev(idx, "neighbor_indices"), _index_args(idx),
                                      _dev(dist, "neighbor_distances"), _dev(pair_values, "pair_values"),
-                                     _dev(mask_u8, "pair_mask"), idx.shape[0], n, c, int(full_list),
+                                     _dev(mask_u8, "pair_mask"), idx.shape[0], _dev(pair_count_of(idx), "pair count"),
+                                     n, c, int(full_list),
                                      ctypes.byref(pot), _dev(out, "out"), _stream()), "tpme_pair_forward")
     _count()
     return out
@@ -802,15 +827,44 @@ def pair_backward(charges, idx, dist, pair_values, mask_u8, grad_out, full_list:
     if g_q is None and want_charges:
         g_q = torch.zeros_like(charges)
     g_p = grad_pairs_out
-    if g_p is None and want_pairs:
-        g_p = torch.empty(idx.shape[0], dtype=charges.dtype, device=charges.device)
+    count = pair_count_of(idx)
+    if g_p is None and want_pairs:    # padding entries of a counted list are not written: zeros there
+        g_p = (torch.empty if count is None else torch.zeros)(idx.shape[0], dtype=charges.dtype, device=charges.device)
     with _on(charges, "charges"):
         _check(lib.tpme_pair_backward(_dtype_id(charges), _dev(charges, "charges"),
                                       _dev(idx, "neighbor_indices"), _index_args(idx),
                                       _dev(dist, "neighbor_distances"), _dev(pair_values, "pair_values"),
                                       _dev(mask_u8, "pair_mask"), _dev(grad_out, "grad_out"),
-                                      idx.shape[0], n, c, int(full_list), ctypes.byref(pot),
+                                      idx.shape[0], _dev(count, "pair count"), n, c, int(full_list),
+                                      ctypes.byref(pot),
                                       _dev(g_q, "grad_charges"), _dev(g_p, "grad_pairs"), _stream()),
                "tpme_pair_backward")
     _count()
     return g_q, g_p
+
+
+def pair_distances(positions, cell_host, idx, shifts, count, out):
+    """out[p] = |r_j + S_p . cell - r_i| (tpme_pair_distances); `count`: device pair count or None"""
+    lib = load()
+    with _on(positions, "positions"):
+        _check(lib.tpme_pair_distances(_dtype_id(positions), _dev(positions, "positions"),
+                                       _mat9(np.asarray(cell_host).reshape(-1)), _dev(idx, "neighbor_indices"),
+                                       _index_args(idx), _dev(shifts, "shifts"), idx.shape[0],
+                                       _dev(count, "pair count"), _dev(out, "distances"), _stream()),
+               "tpme_pair_distances")
+    _count()
+    return out
+
+
+def pair_distances_backward(positions, cell_host, idx, shifts, grad_d, count, grad_positions, grad_cell):
+    lib = load()
+    with _on(positions, "positions"):
+        _check(lib.tpme_pair_distances_backward(_dtype_id(positions), _dev(positions, "positions"),
+                                                _mat9(np.asarray(cell_host).reshape(-1)),
+                                                _dev(idx, "neighbor_indices"), _index_args(idx),
+                                                _dev(shifts, "shifts"), _dev(grad_d, "grad_distances"),
+                                                idx.shape[0], _dev(count, "pair count"),
+                                                _dev(grad_positions, "grad_positions"),
+                                                _dev(grad_cell, "grad_cell"), _stream()),
+               "tpme_pair_distances_backward")
+    _count()

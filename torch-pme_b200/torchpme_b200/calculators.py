@@ -248,6 +248,7 @@ class Calculator(torch.nn.Module):
             kvectors, self._handle)
 
     @torch.jit.unused
+    @torch.compiler.disable   # ctypes launches: torch.compile runs this frame eagerly (one graph break)
     def _forward_impl(self, charges, cell, positions, neighbor_indices, neighbor_distances,
                       periodic=None, node_mask=None, pair_mask=None, kvectors=None):
         validate_parameters(charges, cell, positions, neighbor_indices, neighbor_distances,
@@ -295,6 +296,7 @@ class PMECalculator(Calculator):
         return not any(t.requires_grad for t in list(pot.parameters()) + list(pot.buffers()))
 
     @torch.jit.unused
+    @torch.compiler.disable   # ctypes launches: torch.compile runs this frame eagerly (one graph break)
     def _forward_impl(self, charges, cell, positions, neighbor_indices, neighbor_distances,
                       periodic=None, node_mask=None, pair_mask=None, kvectors=None):
         # the fused node is CUDA only; CPU tensors go through the modular blocks, which dispatch to the

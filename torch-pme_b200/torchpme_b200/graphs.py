@@ -136,3 +136,104 @@ class GraphedStep:
             self.neighbor_distances.copy_(neighbor_distances, non_blocking=True)
         self.graph.replay()
         return self.energy, self.grad_positions, self.grad_distances
+
+
+class GraphedPositionsStep:
+    """
+    Energy and forces from positions alone, as ONE CUDA graph: the neighbor list is rebuilt on the device
+    inside the graph (``neighbors.DeviceNeighborList``: fixed-capacity buffers, the pair count never
+    leaves the device), the distances are tied to the positions by ``neighbors.distances_from`` and the
+    forces collect the mesh part and the real-space part:
+
+        idx, d, S = list.build(positions);  d = distances_from(positions, cell, idx, S)
+        V = calculator(charges, cell, positions, idx, d);  E = sum(q V);  F = -dE/dpositions
+
+    With ``host_io=True`` the graph starts with the H2D copies of positions and charges from the pinned
+    tensors ``.host["positions"]`` / ``.host["charges"]`` and ends with the D2H copies of the energy,
+    ``dE/dpositions`` and the pair count -- 16 + 12 bytes per atom cross PCIe instead of the pair list.
+    ``capacity`` defaults to 1.2 x the pair count of the positions given here; after a step
+    ``overflowed()`` tells whether the list still fitted (a step that overflowed is incomplete: make a
+    new object with a larger capacity).
+    """
+
+    def __init__(self, calculator, charges, cell, positions, cutoff: float, capacity: int | None = None,
+                 host_io: bool = False, warmup: int = 3, index_dtype: torch.dtype = torch.int32):
+        from .neighbors import DeviceNeighborList, neighbor_list
+
+        dev = positions.device
+        if dev.type != "cuda":
+            raise ValueError("GraphedPositionsStep needs CUDA tensors")
+        full = bool(getattr(calculator, "full_neighbor_list", False))
+        if capacity is None:
+            exact = neighbor_list(positions, cell, cutoff, full_neighbor_list=full, index_dtype=index_dtype)[0].shape[0]
+            capacity = int(1.2 * exact) + 1024
+        self.calculator, self.cutoff, self.capacity = calculator, float(cutoff), int(capacity)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.aux = torch.cuda.Stream(device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        nan_check_before = _mesh._nan_check
+        set_nan_check(False)
+        with torch.cuda.stream(self.stream):
+            self.charges = charges.detach().clone()
+            self.cell = cell.detach().clone()
+            self.positions = positions.detach().clone().requires_grad_(True)
+            self.list = DeviceNeighborList(positions.shape[0], self.cell, cutoff, self.capacity, dtype=positions.dtype,
+                                           device=dev, full_neighbor_list=full, index_dtype=index_dtype)
+            self.host = None
+            if host_io:
+                self.host = {
+                    "positions": positions.detach().cpu().pin_memory(),
+                    "charges": charges.detach().cpu().pin_memory(),
+                    "energy": torch.empty((), dtype=positions.dtype).pin_memory(),
+                    "grad_positions": torch.empty(positions.shape, dtype=positions.dtype).pin_memory(),
+                    "n_pairs": torch.zeros((), dtype=torch.int64).pin_memory(),
+                }
+            for _ in range(max(1, warmup)):
+                self._step()
+            self.stream.synchronize()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                if host_io:
+                    with torch.no_grad():
+                        self.positions.copy_(self.host["positions"], non_blocking=True)
+                        self.charges.copy_(self.host["charges"], non_blocking=True)
+                self.energy, self.grad_positions = self._step()
+                if host_io:
+                    self.host["grad_positions"].copy_(self.grad_positions, non_blocking=True)
+                    self.host["energy"].copy_(self.energy, non_blocking=True)
+                    self.host["n_pairs"].copy_(self.list.n_pairs, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        torch.cuda.synchronize(dev)
+        set_nan_check(nan_check_before)
+
+    def _step(self):
+        from .neighbors import distances_from
+
+        idx, d, shifts = self.list.build(self.positions)
+        dist = distances_from(self.positions, self.cell, idx, shifts, known_distances=d)
+        V = self.calculator(self.charges, self.cell, self.positions, idx, dist)
+        main = torch.cuda.current_stream(self.positions.device)
+        self.aux.wait_stream(main)
+        with torch.cuda.stream(self.aux):
+            energy = (V.detach() * self.charges).sum()
+        (g_pos,) = torch.autograd.grad(V, (self.positions,), grad_outputs=self.charges)
+        main.wait_stream(self.aux)
+        return energy, g_pos
+
+    def replay(self) -> None:
+        self.graph.replay()
+
+    def overflowed(self) -> bool:
+        """did the last step's pair list exceed the capacity? (host_io: reads the copied count, no extra sync)"""
+        n = int(self.host["n_pairs"]) if self.host is not None else int(self.list.n_pairs)
+        return n > self.capacity
+
+    @torch.no_grad()
+    def __call__(self, positions=None, charges=None):
+        """copy the given inputs into the static buffers, replay, return ``(energy, dE/dpositions)``"""
+        if positions is not None:
+            self.positions.copy_(positions, non_blocking=True)
+        if charges is not None:
+            self.charges.copy_(charges, non_blocking=True)
+        self.graph.replay()
+        return self.energy, self.grad_positions
