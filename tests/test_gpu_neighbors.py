@@ -216,3 +216,40 @@ def test_graphed_positions_step_matches_the_list_based_step():
             assert not step.overflowed()
             E_ref, g_ref = eager(moved)
             assert rel_err(E, E_ref) < 1e-11 and rel_err(g, g_ref) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("calc_name", ["PMECalculator", "P3MCalculator"])
+def test_forward_from_pairs_equals_the_composition(calc_name, dtype):
+    """calculator.forward_from_pairs(q, cell, r, idx, S) == calculator(q, cell, r, idx, distances_from(r, cell, idx, S)),
+    values and the complete position gradient (mesh + real space), with / without known distances, on an
+    exact-size and on a fixed-capacity list, for a generic upstream gradient"""
+    import torchpme_b200 as tp
+    from torchpme_b200.neighbors import DeviceNeighborList, distances_from, neighbor_list
+
+    pos, q, cell, _, _ = rocksalt(8, dtype=dtype, device="cuda", cutoff=5.0)
+    calc = getattr(tp, calc_name)(tp.CoulombPotential(smearing=1.1).to("cuda"), mesh_spacing=float(cell[0, 0]) / 14)
+    idx, d, s = neighbor_list(pos, cell, 5.0, index_dtype=torch.int32)
+    w = torch.randn(q.shape, dtype=dtype, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+
+    p0 = pos.clone().requires_grad_(True)
+    q0 = q.clone().requires_grad_(True)
+    V0 = calc(q0, cell, p0, idx, distances_from(p0, cell, idx, s))
+    gp0, gq0 = torch.autograd.grad(V0, (p0, q0), grad_outputs=w)
+    tol = 1e-11 if dtype == torch.float64 else 3e-5
+    nl = DeviceNeighborList(pos.shape[0], cell, 5.0, capacity=idx.shape[0] + 500, dtype=dtype)
+    ci, cd, cs = nl.build(pos)
+    for (i_, s_, known) in ((idx, s, None), (idx, s, d), (ci, cs, cd), (ci, cs, None)):
+        p1 = pos.clone().requires_grad_(True)
+        q1 = q.clone().requires_grad_(True)
+        V1 = calc.forward_from_pairs(q1, cell, p1, i_, s_, known_distances=known)
+        gp1, gq1 = torch.autograd.grad(V1, (p1, q1), grad_outputs=w)
+        assert rel_err(V1.detach(), V0.detach()) < tol
+        assert rel_err(gp1, gp0) < tol and rel_err(gq1, gq0) < tol
+    # forces only (no charge gradient) and charges only
+    p1 = pos.clone().requires_grad_(True)
+    (gp1,) = torch.autograd.grad(calc.forward_from_pairs(q, cell, p1, idx, s), p1, grad_outputs=w)
+    assert rel_err(gp1, gp0) < tol
+    q1 = q.clone().requires_grad_(True)
+    (gq1,) = torch.autograd.grad(calc.forward_from_pairs(q1, cell, pos, idx, s), q1, grad_outputs=w)
+    assert rel_err(gq1, gq0) < tol

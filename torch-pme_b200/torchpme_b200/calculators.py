@@ -112,21 +112,30 @@ class _FusedMeshPotential(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, charges, positions, distances, neighbor_indices, mask_u8, cfg):
+    def forward(ctx, charges, positions, distances, neighbor_indices, mask_u8, cfg, shifts=None, cell_host=None):
         q = charges.detach().contiguous()
         pos = positions.detach().contiguous()
-        d = distances.detach().contiguous()
         idx = neighbor_indices.contiguous()
         need_pos = ctx.needs_input_grad[1]
         out = torch.empty_like(q)
+        # `shifts` given: the distances are |r_j + S . cell - r_i| of THESE positions (forward_from_pairs):
+        # they are computed on the real-space branch unless the caller already has them, and the backward
+        # carries dL/dd on to the positions on that branch too
+        ctx.shifts, ctx.cell_host = shifts, cell_host
+        d = None if distances is None else distances.detach().contiguous()
         # the pair sum is independent of the mesh pipeline until the gather epilogue: run it (and
         # the zero fill of its accumulator) on a side stream -- a parallel branch when the step is
         # captured in a CUDA graph.  `out` is next touched on the main stream after the join.
         main = torch.cuda.current_stream(q.device)
         side = _side_stream(q.device)
         side.wait_stream(main)
+        need_dist = d is None
+        if need_dist:       # allocated on the main stream like `out`: both branches join before anything is freed
+            d = torch.zeros(idx.shape[0], dtype=q.dtype, device=q.device)
         with torch.cuda.stream(side):
             out.zero_()
+            if need_dist:
+                _native.pair_distances(pos, cell_host, idx, shifts, _native.pair_count_of(idx), d)
             _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
         # atoms binned by mesh tile once per step: the spread, the gather and both backward launches
         # stage their pencil of the mesh in shared memory (csrc/tiles.cu); None = direct kernels
@@ -148,6 +157,9 @@ class _FusedMeshPotential(torch.autograd.Function):
         q, pos, d, idx, mask_u8, dvalues = ctx.saved_tensors
         cfg, tiles = ctx.cfg, ctx.tiles
         need_q, need_pos, need_d = ctx.needs_input_grad[:3]
+        shifts = ctx.shifts
+        if shifts is not None:           # distances derived from the positions: dL/dd ends in dL/dpositions
+            need_d = need_pos
         g = grad_out.contiguous()
         g_q = torch.zeros_like(q) if need_q else None
         g_d = None
@@ -157,13 +169,22 @@ class _FusedMeshPotential(torch.autograd.Function):
         if need_q or need_d:
             # dL/dd is produced by the pair kernel alone -> side stream; when dL/dq is wanted too the
             # gather epilogue accumulates into the same buffer, so the join happens before it
-            g_d = torch.empty(idx.shape[0], dtype=q.dtype, device=q.device) if need_d else None
+            g_d = None
+            if need_d:     # padding entries of a counted (fixed-capacity) list are never written: zeros there
+                counted = _native.pair_count_of(idx) is not None
+                g_d = (torch.zeros if counted else torch.empty)(idx.shape[0], dtype=q.dtype, device=q.device)
+            g_pos4 = None
+            if shifts is not None and need_d:
+                g_pos4 = torch.zeros((pos.shape[0], 4), dtype=q.dtype, device=q.device)
             side.wait_stream(main)
             forked = True
             with torch.cuda.stream(side):
                 _native.pair_backward(q, idx, d, None, mask_u8, g, cfg.full_list, cfg.pair_pot,
                                       want_charges=need_q, want_pairs=need_d, grad_charges_out=g_q,
                                       grad_pairs_out=g_d)
+                if g_pos4 is not None:
+                    _native.pair_distances_backward(pos, ctx.cell_host, idx, shifts, g_d,
+                                                    _native.pair_count_of(idx), g_pos4, None)
         g_pos = None
         if need_q or need_pos:
             rho_g = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
@@ -183,7 +204,11 @@ class _FusedMeshPotential(torch.autograd.Function):
                                tiles=tiles)
         if forked:
             main.wait_stream(side)
-        return g_q, g_pos, g_d, None, None, None
+        if shifts is not None:
+            if need_d:
+                g_pos = g_pos4[:, :3] if g_pos is None else g_pos + g_pos4[:, :3]
+            g_d = None
+        return g_q, g_pos, g_d, None, None, None, None, None
 
 
 class Calculator(torch.nn.Module):
@@ -309,7 +334,35 @@ class PMECalculator(Calculator):
         cfg = self._fused_config(cell)
         mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
         return _FusedMeshPotential.apply(charges, positions, neighbor_distances, neighbor_indices,
-                                         mask_u8, cfg)
+                                         mask_u8, cfg, None, None)
+
+    def forward_from_pairs(self, charges, cell, positions, neighbor_indices, neighbor_shifts,
+                           known_distances=None, pair_mask=None):
+        """
+        ``forward`` for a pair list given as indices + integer image shifts (what a neighbor search returns:
+        ``neighbors.neighbor_list``, vesin's ``"PS"`` quantities): equal to
+
+            d = neighbors.distances_from(positions, cell, neighbor_indices, neighbor_shifts)
+            V = self(charges, cell, positions, neighbor_indices, d)
+
+        including the gradient that reaches ``positions`` through the distances -- but on the fast path the
+        distance kernels run on the real-space branch of the step, next to the pair kernels and concurrent
+        with the mesh pipeline, instead of as separate autograd nodes around it.  ``known_distances``: the
+        distances of these very positions when the caller has them already (skips their evaluation).
+        """
+        from .neighbors import distances_from
+
+        if positions.is_cuda and not cell.requires_grad and self._fast_path_ok(cell, None, None, None):
+            validate_parameters(charges, cell, positions, neighbor_indices,
+                                known_distances if known_distances is not None else
+                                torch.empty(neighbor_indices.shape[0], dtype=positions.dtype, device=positions.device),
+                                None, pair_mask, None, None)
+            cfg = self._fused_config(cell)
+            mask_u8 = None if pair_mask is None else pair_mask.contiguous().view(torch.uint8)
+            return _FusedMeshPotential.apply(charges, positions, known_distances, neighbor_indices, mask_u8, cfg,
+                                             neighbor_shifts.contiguous(), geometry_of(cell).cell)
+        d = distances_from(positions, cell, neighbor_indices, neighbor_shifts, known_distances=known_distances)
+        return self(charges, cell, positions, neighbor_indices, d, pair_mask=pair_mask)
 
     def _fused_config(self, cell) -> _FusedStepConfig:
         """by-value launch parameters of the fast path, cached per (cell geometry, potential scalars)"""

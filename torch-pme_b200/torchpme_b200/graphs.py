@@ -207,12 +207,24 @@ class GraphedPositionsStep:
         set_nan_check(nan_check_before)
 
     def _step(self):
-        from .neighbors import distances_from
+        from .calculators import _side_stream
 
-        idx, d, shifts = self.list.build(self.positions)
-        dist = distances_from(self.positions, self.cell, idx, shifts, known_distances=d)
-        V = self.calculator(self.charges, self.cell, self.positions, idx, dist)
+        # the list is built on the real-space branch of the step (the stream the calculator runs its pair
+        # kernels on): the mesh pipeline, which only needs positions and charges, does not wait for it
         main = torch.cuda.current_stream(self.positions.device)
+        side = _side_stream(self.positions.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            idx, d, shifts = self.list.build(self.positions)
+        if hasattr(self.calculator, "forward_from_pairs"):
+            V = self.calculator.forward_from_pairs(self.charges, self.cell, self.positions, idx, shifts,
+                                                   known_distances=d)
+        else:
+            from .neighbors import distances_from
+
+            main.wait_stream(side)
+            dist = distances_from(self.positions, self.cell, idx, shifts, known_distances=d)
+            V = self.calculator(self.charges, self.cell, self.positions, idx, dist)
         self.aux.wait_stream(main)
         with torch.cuda.stream(self.aux):
             energy = (V.detach() * self.charges).sum()
