@@ -169,7 +169,8 @@ typedef struct tpme_green {
   int kind;
   int exponent;
   int p3m_nodes;
-  int reserved;
+  int p3m_mode;        /* low byte: influence-function mode 0..3 (lib/kspace_filter.py:307-329); for modes 1..3 the
+                          next byte is the order 1..6 of the differential operator (:331-347) */
   double smearing;
   double prefactor;
   double scale;

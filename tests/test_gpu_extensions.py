@@ -127,3 +127,33 @@ def test_torch_compile_wraps_the_calculator():
         assert type(out) is torch.Tensor and rel_err(out, ref) < 1e-5
         (out * q).sum().backward()
         assert p.grad is not None and torch.isfinite(p.grad).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("mode, order", [(1, 1), (1, 2), (2, 4), (3, 6), (0, 2)])
+@pytest.mark.parametrize("triclinic", [False, True])
+def test_p3m_influence_modes_in_kernel(mode, order, triclinic, dtype):
+    """P3MKSpaceFilter modes 1-3 (lib/kspace_filter.py:307-347) evaluated per k-point inside the filter kernel
+    against the table route (the reference's torch expression, CPU-checked against the reference in
+    test_spline_potentials.py) and against the package's CPU path"""
+    import torchpme_b200 as tp
+
+    gen = torch.Generator().manual_seed(mode * 10 + order)
+    cell = torch.eye(3, dtype=torch.float64) * 9.0
+    if triclinic:
+        cell = cell + 0.8 * torch.rand(3, 3, generator=gen, dtype=torch.float64)
+    ns = torch.tensor([16, 32, 16])
+    pot = tp.CoulombPotential(smearing=0.9)
+    mesh = torch.randn((2, 16, 32, 16), generator=gen, dtype=torch.float64)
+    f_cpu = tp.P3MKSpaceFilter(cell.to(dtype), ns, 4, pot, mode=mode, differential_order=order)
+    want = f_cpu(mesh.to(dtype))
+    f_gpu = tp.P3MKSpaceFilter(cell.to("cuda", dtype), ns.cuda(), 4, pot.to("cuda"), mode=mode, differential_order=order)
+    assert not f_gpu._wants_table()
+    got = f_gpu(mesh.to("cuda", dtype))
+    c_grad = cell.to("cuda", dtype).requires_grad_(True)          # forces the differentiable table route
+    f_tab = tp.P3MKSpaceFilter(c_grad, ns.cuda(), 4, pot.to("cuda"), mode=mode, differential_order=order)
+    assert f_tab._wants_table()
+    tab = f_tab(mesh.to("cuda", dtype)).detach()
+    tol = 1e-10 if dtype == torch.float64 else 2e-4
+    assert rel_err(got, tab) < tol
+    assert rel_err(got.cpu(), want) < tol

@@ -72,9 +72,20 @@ __device__ T gammaincc_over_powerlaw_dev(int p, T z) {
   }
 }
 
+// coefficients of the finite-difference approximations to ik (kspace_filter.py:282-293), row = order - 1
+__device__ __constant__ const double kP3MDiffCoeff[6][6] = {
+    {1.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {4.0 / 3, -1.0 / 3, 0.0, 0.0, 0.0, 0.0},
+    {3.0 / 2, -3.0 / 5, 1.0 / 10, 0.0, 0.0, 0.0},
+    {8.0 / 5, -4.0 / 5, 8.0 / 35, -1.0 / 35, 0.0, 0.0},
+    {5.0 / 3, -20.0 / 21, 5.0 / 14, -5.0 / 63, 1.0 / 126, 0.0},
+    {12.0 / 7, -15.0 / 14, 10.0 / 21, -1.0 / 7, 2.0 / 77, -1.0 / 465},
+};
+
 template <typename T>
 struct GreenDev {
   int kind, exponent, p3m_nodes;
+  int p3m_mode, diff_order;   // P3M influence function of modes 1..3 with a differential operator of order 1..6
   T recip[9];
   T spacing[3];
   T half_s2;      // smearing^2 / 2
@@ -117,7 +128,28 @@ __device__ __forceinline__ T green_value(const GreenDev<T>& g, int ix, int iy, i
     T u2 = T(1);
     const T s2 = s * s;
     for (int i = 0; i < g.p3m_nodes; ++i) u2 *= s2;
-    val = (u2 == T(0)) ? T(0) : val / u2;
+    if (g.p3m_mode == 0) {
+      val = (u2 == T(0)) ? T(0) : val / u2;
+    } else {
+      // (k . D)^mode / (U^2 |D|^(4 mode)),  D_a = sum_i c_i / (i + 1) sin((i + 1) k_a h_a) / h_a
+      // (kspace_filter.py:318-347; eq. 30 of doi:10.1063/1.3000389)
+      const T kk[3] = {kx, ky, kz};
+      T d_sq = T(0), k_dot_d = T(0);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const T kh = kk[a] * g.spacing[a];
+        T acc = T(0);
+        for (int i = 0; i < g.diff_order; ++i)
+          acc += (T)(kP3MDiffCoeff[g.diff_order - 1][i] / (i + 1)) * M::sin(kh * T(i + 1));
+        const T d = acc / g.spacing[a];
+        d_sq += d * d;
+        k_dot_d += kk[a] * d;
+      }
+      T numer = T(1), d4 = T(1);
+      for (int i = 0; i < g.p3m_mode; ++i) { numer *= k_dot_d; d4 *= d_sq * d_sq; }
+      const T denom = u2 * d4;
+      val = (denom == T(0)) ? T(0) : val * numer / denom;
+    }
   }
   return val;
 }
@@ -128,6 +160,8 @@ inline GreenDev<T> make_green(const tpme_green* h) {
   g.kind = h->kind;
   g.exponent = h->exponent;
   g.p3m_nodes = h->p3m_nodes;
+  g.p3m_mode = h->p3m_mode & 255;
+  g.diff_order = (h->p3m_mode >> 8) & 255;
   for (int i = 0; i < 9; ++i) g.recip[i] = (T)h->recip[i];
   for (int i = 0; i < 3; ++i) g.spacing[i] = (T)h->spacing[i];
   const double s2 = h->smearing * h->smearing;
@@ -156,6 +190,8 @@ inline int check_green(const tpme_green* g) {
   TPME_REQUIRE(g->kind != 0 || g->table != nullptr, "table kind needs a table pointer");
   TPME_REQUIRE(g->kind != 2 || (g->exponent >= 1 && g->exponent <= 6), "Unsupported exponent");
   TPME_REQUIRE(g->p3m_nodes >= 0 && g->p3m_nodes <= 7, "bad p3m_nodes");
+  TPME_REQUIRE((g->p3m_mode & 255) <= 3 && ((g->p3m_mode & 255) == 0 || (((g->p3m_mode >> 8) & 255) >= 1 && ((g->p3m_mode >> 8) & 255) <= 6)),
+               "P3M mode must be 0..3 with a differential order 1..6");
   return 0;
 }
 

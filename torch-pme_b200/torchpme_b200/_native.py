@@ -37,7 +37,7 @@ class _Green(ctypes.Structure):
         ("kind", ctypes.c_int),
         ("exponent", ctypes.c_int),
         ("p3m_nodes", ctypes.c_int),
-        ("reserved", ctypes.c_int),
+        ("p3m_mode", ctypes.c_int),
         ("smearing", ctypes.c_double),
         ("prefactor", ctypes.c_double),
         ("scale", ctypes.c_double),
@@ -522,9 +522,10 @@ def get_plan(dtype, ns, batch, device) -> FFTPlan:
 
 
 def make_green(kind, scale, recip, spacing=(0.0, 0.0, 0.0), smearing=1.0, prefactor=1.0,
-               exponent=1, p3m_nodes=0, table=None) -> _Green:
+               exponent=1, p3m_nodes=0, table=None, p3m_mode=0, differential_order=2) -> _Green:
     g = _Green()
     g.kind, g.exponent, g.p3m_nodes = int(kind), int(exponent), int(p3m_nodes)
+    g.p3m_mode = int(p3m_mode) | (int(differential_order) << 8 if p3m_mode else 0)
     g.smearing, g.prefactor, g.scale = float(smearing), float(prefactor), float(scale)
     for k in range(9):
         g.recip[k] = float(recip[k])

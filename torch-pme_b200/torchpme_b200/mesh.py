@@ -559,6 +559,9 @@ class KSpaceFilter(torch.nn.Module):
     def _p3m_nodes(self) -> int:
         return 0
 
+    def _p3m_mode(self) -> dict:
+        return {}
+
     def _wants_table(self) -> bool:
         descriptor = getattr(self.kernel, "_native_descriptor", lambda: None)()
         if descriptor is None or self.cell.requires_grad:
@@ -605,7 +608,8 @@ class KSpaceFilter(torch.nn.Module):
             smearing, prefactor = self.kernel._scalars()
             cfg = _FilterConfig(dict(kind=kind, exponent=exponent, smearing=smearing,
                                      prefactor=prefactor, recip=geom.recip,
-                                     spacing=geom.spacing(ns), p3m_nodes=self._p3m_nodes()), scale)
+                                     spacing=geom.spacing(ns), p3m_nodes=self._p3m_nodes(),
+                                     **self._p3m_mode()), scale)
             result = _KFilter.apply(mesh_values, None, cfg)
         if _nan_check and not torch.cuda.is_current_stream_capturing():
             if torch.isnan(result).any():
@@ -621,7 +625,9 @@ class KSpaceFilter(torch.nn.Module):
 class P3MKSpaceFilter(KSpaceFilter):
     """
     Filter with the P3M influence function folded in (reference: ``lib/kspace_filter.py:225-363``).
-    Mode 0 (point-charge potential) is evaluated in-kernel; modes 1-3 use the table route.
+    All modes (0: point-charge potential; 1-3 with the finite-difference operator of order 1-6) are evaluated
+    per k-point inside the filter kernel (``csrc/green.cuh``); the torch table ``_influence`` below serves
+    the differentiable route (cell / parameter gradients) and the CPU path.
     """
 
     _DIFF_COEFF = (
@@ -650,8 +656,8 @@ class P3MKSpaceFilter(KSpaceFilter):
     def _p3m_nodes(self) -> int:
         return self.interpolation_nodes
 
-    def _wants_table(self) -> bool:
-        return self.mode != 0 or super()._wants_table()
+    def _p3m_mode(self) -> dict:
+        return dict(p3m_mode=self.mode, differential_order=self.differential_order)
 
     def _influence(self, kvectors):
         ns = self._ns()
