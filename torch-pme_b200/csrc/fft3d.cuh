@@ -519,28 +519,48 @@ rows_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int64_t n_row
   // un-split straight from global memory (natural order in buf2):
   //   Z'[k] = (X[k] + conj X[H-k]) + i conj(w^k) (X[k] - conj X[H-k])
   const C2<T>* src = in + row0 * P;
-  for (int i = tid; i < rows * (H / 2 + 1); i += nt) {
-    const int r = i / (H / 2 + 1), k = i - r * (H / 2 + 1);
-    const C2<T>* irow = src + (int64_t)r * P;
-    C2<T>* row = buf2 + r * P;
-    if (k == 0) {
-      const T x0 = irow[0].x, xh = irow[H].x;
-      row[0] = {x0 + xh, x0 - xh};
-    } else {
-      const int kk = H - k;
-      const C2<T> xk = irow[k], xkk = irow[kk];
-      const C2<T> w = tw[k];
-      {
-        const C2<T> s = {xk.x + xkk.x, xk.y - xkk.y};          // X[k] + conj X[H-k]
-        const C2<T> d = {xk.x - xkk.x, xk.y + xkk.y};          // X[k] - conj X[H-k]
-        const C2<T> wd = {d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y};   // conj(w) d
-        row[k] = {s.x - wd.y, s.y + wd.x};                     // s + i wd
+  {
+    // four (X[k], X[H-k]) pairs per thread are in flight before the first one is consumed (the loop with
+    // one pair per iteration stalled on its two loads: long_scoreboard 8.4 in profiles/r02_ncu_full_c4.csv)
+    constexpr int U = 4, KH = H / 2 + 1;
+    const int total = rows * KH;
+    for (int i0 = tid; i0 < total; i0 += U * nt) {
+      C2<T> xa[U], xb[U];
+      int rr[U], kq[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nt;
+        rr[u] = i / KH;
+        kq[u] = i - rr[u] * KH;
+        if (i < total) {
+          const C2<T>* irow = src + (int64_t)rr[u] * P;
+          xa[u] = irow[kq[u]];
+          xb[u] = irow[H - kq[u]];
+        }
       }
-      if (kk != k) {
-        const C2<T> s = {xkk.x + xk.x, xkk.y - xk.y};
-        const C2<T> d = {xkk.x - xk.x, xkk.y + xk.y};
-        const C2<T> wd = {-(d.x * w.x - d.y * w.y), -(d.x * w.y + d.y * w.x)};   // conj(w^{H-k}) = -w^k
-        row[kk] = {s.x - wd.y, s.y + wd.x};
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i0 + u * nt >= total) break;
+        const int k = kq[u], kk = H - k;
+        C2<T>* row = buf2 + rr[u] * P;
+        const C2<T> xk = xa[u], xkk = xb[u];
+        if (k == 0) {
+          row[0] = {xk.x + xkk.x, xk.x - xkk.x};                 // X[0], X[H] are real
+          continue;
+        }
+        const C2<T> w = tw[k];
+        {
+          const C2<T> s = {xk.x + xkk.x, xk.y - xkk.y};          // X[k] + conj X[H-k]
+          const C2<T> d = {xk.x - xkk.x, xk.y + xkk.y};          // X[k] - conj X[H-k]
+          const C2<T> wd = {d.x * w.x + d.y * w.y, d.y * w.x - d.x * w.y};   // conj(w) d
+          row[k] = {s.x - wd.y, s.y + wd.x};                     // s + i wd
+        }
+        if (kk != k) {
+          const C2<T> s = {xkk.x + xk.x, xkk.y - xk.y};
+          const C2<T> d = {xkk.x - xk.x, xkk.y + xk.y};
+          const C2<T> wd = {-(d.x * w.x - d.y * w.y), -(d.x * w.y + d.y * w.x)};   // conj(w^{H-k}) = -w^k
+          row[kk] = {s.x - wd.y, s.y + wd.x};
+        }
       }
     }
   }
