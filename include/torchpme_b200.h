@@ -162,7 +162,11 @@ int tpme_rfft3(tpme_fft_plan plan, const void* mesh, void* mesh_hat, void* strea
 int tpme_irfft3(tpme_fft_plan plan, void* mesh_hat /* destroyed */, void* mesh, void* stream);
 
 /* Green's function description.  kind: 0 = table (device pointer, (nx,ny,nz/2+1) reals),
- * 1 = Coulomb, 2 = inverse power law with `exponent` in 1..6.  `p3m_nodes` > 0 multiplies
+ * 1 = Coulomb, 2 = inverse power law with `exponent` in 1..6, 3 = cubic spline in k^2 (SplinePotential,
+ * potentials/spline.py:108-121,151-157; lib/splines.py CubicSpline): `table` = device doubles
+ * [x(n), y(n), y''(n)], `exponent` = n; 4 = the same on a reciprocal axis (CubicSplineReciprocal): `table` =
+ * [1/x knots incl. 0 (n), y (n), y'' (n)] followed by the three-knot head spline [x(3), y(3), y''(3)] used below
+ * the first grid point.  G = prefactor * spline(k^2).  `p3m_nodes` > 0 multiplies
  * the mode-0 P3M influence function 1/U^2 for that interpolation order.  `scale`
  * multiplies the result (FFT normalisation, prefactors). */
 typedef struct tpme_green {

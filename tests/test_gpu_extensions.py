@@ -177,3 +177,48 @@ def test_p3m_influence_modes_in_kernel(mode, order, triclinic, dtype):
         mesh = torch.randn((2,) + ns, generator=gen, dtype=torch.float64).to("cuda", dtype)
         a, b = f_gpu(mesh), f_tab(mesh).detach()
         assert rel_err(a, b) < (1e-10 if dtype == torch.float64 else 2e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("reciprocal", [True, False], ids=["reciprocal-axis", "direct"])
+@pytest.mark.parametrize("p3m", [False, True], ids=["pme", "p3m"])
+def test_spline_kernel_evaluated_in_the_filter_kernel(p3m, reciprocal, dtype):
+    """SplinePotential.lr_from_k_sq (potentials/spline.py:151-157: cubic spline in k^2, direct or on a reciprocal
+    axis) evaluated per k-point inside the filter kernel (green kinds 3 / 4) against the table the potential's
+    own torch code builds; triclinic cell, a mesh that reaches below the first and beyond the last knot"""
+    import math
+
+    import torchpme_b200 as tp
+    from torchpme_b200 import _native
+    from torchpme_b200.lib import KSpaceFilter, P3MKSpaceFilter
+    from torchpme_b200.mesh import geometry_of
+
+    smearing = 1.0
+    if reciprocal:
+        r = torch.logspace(-2, 2, 400, dtype=torch.float64)
+        y = torch.erf(r / smearing / 2 ** 0.5) / r
+        pot = tp.SplinePotential(r, y, reciprocal=True, y_at_zero=math.sqrt(2 / math.pi) / smearing,
+                                 yhat_at_zero=0.0, smearing=smearing, prefactor=1.7)
+    else:
+        r = torch.linspace(0.0, 12.0, 300, dtype=torch.float64)
+        y = torch.exp(-0.5 * (r / 1.3) ** 2)
+        k = torch.linspace(0.0, 9.0, 200, dtype=torch.float64)
+        pot = tp.SplinePotential(r, y, k_grid=k, smearing=smearing, prefactor=0.6)
+    pot = pot.to("cuda")
+    gen = torch.Generator().manual_seed(7)
+    cell = (torch.eye(3, dtype=torch.float64) * 8.0 + 0.7 * torch.rand(3, 3, generator=gen, dtype=torch.float64)).to("cuda", dtype)
+    ns = (16, 32, 16)
+    make = (lambda c: P3MKSpaceFilter(c, torch.tensor(ns).cuda(), 4, pot, fft_norm="backward", ifft_norm="forward")) \
+        if p3m else (lambda c: KSpaceFilter(c, torch.tensor(ns).cuda(), pot, fft_norm="backward", ifft_norm="forward"))
+    f_gpu, f_tab = make(cell), make(cell.clone().requires_grad_(True))
+    assert not f_gpu._wants_table() and f_tab._wants_table()
+    want = f_tab._kfilter.detach()
+    geom = geometry_of(f_gpu.cell)
+    green = _native.make_green(scale=1.0, recip=geom.recip, spacing=geom.spacing(ns), p3m_nodes=4 if p3m else 0,
+                               **pot._native_filter())
+    assert green.kind == (4 if reciprocal else 3)
+    got = _native.green_table(dtype, ns, green, "cuda")
+    tol = 1e-11 if dtype == torch.float64 else 3e-5
+    assert float((got - want.to(dtype)).abs().max() / want.abs().max()) < tol
+    mesh = torch.randn((2,) + ns, generator=gen, dtype=torch.float64).to("cuda", dtype)
+    assert rel_err(f_gpu(mesh), f_tab(mesh).detach()) < (1e-10 if dtype == torch.float64 else 2e-4)

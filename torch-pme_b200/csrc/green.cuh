@@ -72,6 +72,38 @@ __device__ T gammaincc_over_powerlaw_dev(int p, T z) {
   }
 }
 
+// Natural cubic spline through (x, y) with second derivatives m, n knots, evaluated like
+// lib/splines.py:CubicSpline.forward (interval = searchsorted(x, q, right=True) - 1 clamped to [0, n-2],
+// so the end intervals extrapolate):  a y_i + b y_{i+1} + ((a^3 - a) m_i + (b^3 - b) m_{i+1}) h^2 / 6
+__device__ __forceinline__ double cubic_spline_dev(const double* __restrict__ x, const double* __restrict__ y,
+                                                   const double* __restrict__ m, int n, double q) {
+  int lo = 0, hi = n;                       // first knot > q
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(x + mid) <= q) lo = mid + 1; else hi = mid;
+  }
+  int i = lo - 1;
+  i = i < 0 ? 0 : (i > n - 2 ? n - 2 : i);
+  const double x0 = __ldg(x + i), x1 = __ldg(x + i + 1);
+  const double h = x1 - x0;
+  const double a = (x1 - q) / h, b = 1.0 - a;
+  const double curvature = (a * (a * a - 1.0)) * __ldg(m + i) + (b * (b * b - 1.0)) * __ldg(m + i + 1);
+  return a * __ldg(y + i) + b * __ldg(y + i + 1) + curvature * (h * h / 6.0);
+}
+
+// SplinePotential's reciprocal-space kernel (potentials/spline.py:108-121,151-157) at k^2 = q.
+// kind 3: one spline over k^2, table = [x(n), y(n), m(n)].
+// kind 4: spline on the 1/k^2 axis (lib/splines.py:CubicSplineReciprocal): table = [xi(n), yi(n), mi(n)] of
+//         the inverse-axis spline (its first knot is 1/x = 0) followed by the three-knot head spline
+//         [xh(3), yh(3), mh(3)] that takes over below the first grid point xh[1].
+__device__ __forceinline__ double spline_kernel_dev(int kind, const double* __restrict__ t, int n, double q) {
+  if (kind == 3) return cubic_spline_dev(t, t + n, t + 2 * n, n, q);
+  const double* head = t + 3 * n;
+  const double first = __ldg(head + 1);
+  if (q < first) return cubic_spline_dev(head, head + 3, head + 6, 3, q);
+  return cubic_spline_dev(t, t + n, t + 2 * n, n, 1.0 / q);
+}
+
 // coefficients of the finite-difference approximations to ik (kspace_filter.py:282-293), row = order - 1
 __device__ __constant__ const double kP3MDiffCoeff[6][6] = {
     {1.0, 0.0, 0.0, 0.0, 0.0, 0.0},
@@ -109,7 +141,10 @@ __device__ __forceinline__ T green_value(const GreenDev<T>& g, int ix, int iy, i
   const T kz = fx * g.recip[2] + fy * g.recip[5] + fz * g.recip[8];
   const T k_sq = kx * kx + ky * ky + kz * kz;
   T val;
-  if (k_sq == T(0)) {
+  if (g.kind >= 3) {
+    // tabulated kernel: cubic spline in k^2 (double arithmetic, the tables are double)
+    val = g.amplitude * (T)spline_kernel_dev(g.kind, reinterpret_cast<const double*>(g.table), g.exponent, (double)k_sq);
+  } else if (k_sq == T(0)) {
     val = g.k0_value;
   } else if (g.kind == 1 || g.exponent == 1) {
     // 4 pi exp(-s^2 k^2 / 2) / k^2   (coulomb.py:137-142); IPL p=1 is identical
@@ -171,6 +206,8 @@ inline GreenDev<T> make_green(const tpme_green* h) {
   double amp = h->scale, k0 = 0.0;
   if (h->kind == 1) {
     amp *= h->prefactor * 4.0 * pi;
+  } else if (h->kind >= 3) {
+    amp *= h->prefactor;
   } else if (h->kind == 2) {
     // prefac = pi^1.5 / Gamma(p/2) (2 s^2)^((3-p)/2)   (inversepowerlaw.py:121-125)
     const double p = h->exponent;
@@ -186,8 +223,10 @@ inline GreenDev<T> make_green(const tpme_green* h) {
 
 inline int check_green(const tpme_green* g) {
   TPME_REQUIRE(g != nullptr, "green parameters missing");
-  TPME_REQUIRE(g->kind >= 0 && g->kind <= 2, "green kind must be 0 (table), 1 (coulomb) or 2 (ipl)");
-  TPME_REQUIRE(g->kind != 0 || g->table != nullptr, "table kind needs a table pointer");
+  TPME_REQUIRE(g->kind >= 0 && g->kind <= 4,
+               "green kind must be 0 (table), 1 (coulomb), 2 (ipl), 3 (spline) or 4 (reciprocal-axis spline)");
+  TPME_REQUIRE((g->kind != 0 && g->kind < 3) || g->table != nullptr, "table / spline kinds need a table pointer");
+  TPME_REQUIRE(g->kind < 3 || g->exponent >= 2, "spline kinds carry the number of knots (>= 2) in `exponent`");
   TPME_REQUIRE(g->kind != 2 || (g->exponent >= 1 && g->exponent <= 6), "Unsupported exponent");
   TPME_REQUIRE(g->p3m_nodes >= 0 && g->p3m_nodes <= 7, "bad p3m_nodes");
   TPME_REQUIRE((g->p3m_mode & 255) <= 3 && ((g->p3m_mode & 255) == 0 || (((g->p3m_mode >> 8) & 255) >= 1 && ((g->p3m_mode >> 8) & 255) <= 6)),

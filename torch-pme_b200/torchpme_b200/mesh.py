@@ -212,6 +212,11 @@ class _FilterConfig:
         self.green_args, self.scale = green_args, scale
 
 
+def _green_args(cfg: _FilterConfig, table):
+    """the filter table (kind 0) is an autograd input; spline kinds carry their own knot table in the config"""
+    return cfg.green_args if table is None else dict(cfg.green_args, table=table)
+
+
 class _KFilter(torch.autograd.Function):
     """out = scale * irfft3(G * rfft3(mesh)) with unnormalised transforms (self-adjoint)."""
 
@@ -220,7 +225,7 @@ class _KFilter(torch.autograd.Function):
         mesh_c = mesh.detach().contiguous()
         need_table = table is not None and ctx.needs_input_grad[1]
         table_c = table.detach().contiguous() if table is not None else None
-        green = _native.make_green(table=table_c, scale=cfg.scale, **cfg.green_args)
+        green = _native.make_green(scale=cfg.scale, **_green_args(cfg, table_c))
         out, x_hat = _native.kfilter_apply(mesh_c, green, keep_hat=need_table)
         ctx.cfg = cfg
         ctx.save_for_backward(table_c, x_hat)
@@ -235,7 +240,7 @@ class _KFilter(torch.autograd.Function):
         g = grad_out.contiguous()
         g_mesh = g_table = None
         if need_mesh:
-            green = _native.make_green(table=table_c, scale=cfg.scale, **cfg.green_args)
+            green = _native.make_green(scale=cfg.scale, **_green_args(cfg, table_c))
             g_mesh, g_hat = _native.kfilter_apply(g, green, keep_hat=need_table)
         elif need_table:
             g_hat = _native.rfft3(g)
@@ -563,10 +568,11 @@ class KSpaceFilter(torch.nn.Module):
         return {}
 
     def _wants_table(self) -> bool:
-        descriptor = getattr(self.kernel, "_native_descriptor", lambda: None)()
-        if descriptor is None or self.cell.requires_grad:
+        if self.cell.requires_grad:
             return True
-        return any(t.requires_grad for t in list(self.kernel.parameters()) + list(self.kernel.buffers()))
+        if any(t.requires_grad for t in list(self.kernel.parameters()) + list(self.kernel.buffers())):
+            return True
+        return getattr(self.kernel, "_native_filter", lambda: None)() is None
 
     def forward(self, mesh_values: torch.Tensor) -> torch.Tensor:
         if torch.jit.is_scripting():
@@ -604,12 +610,8 @@ class KSpaceFilter(torch.nn.Module):
             cfg = _FilterConfig(dict(kind=_native.GREEN_TABLE, recip=geom.recip), scale)
             result = _KFilter.apply(mesh_values, table, cfg)
         else:
-            kind, exponent = self.kernel._native_descriptor()
-            smearing, prefactor = self.kernel._scalars()
-            cfg = _FilterConfig(dict(kind=kind, exponent=exponent, smearing=smearing,
-                                     prefactor=prefactor, recip=geom.recip,
-                                     spacing=geom.spacing(ns), p3m_nodes=self._p3m_nodes(),
-                                     **self._p3m_mode()), scale)
+            cfg = _FilterConfig(dict(recip=geom.recip, spacing=geom.spacing(ns), p3m_nodes=self._p3m_nodes(),
+                                     **self._p3m_mode(), **self.kernel._native_filter()), scale)
             result = _KFilter.apply(mesh_values, None, cfg)
         if _nan_check and not torch.cuda.is_current_stream_capturing():
             if torch.isnan(result).any():

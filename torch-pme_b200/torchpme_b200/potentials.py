@@ -140,6 +140,18 @@ class Potential(torch.nn.Module):
         """``None`` (generic torch route) or ``(green_kind, exponent)`` for in-kernel evaluation."""
         return None
 
+    def _native_filter(self):
+        """
+        ``None`` (the filter is a table built from :meth:`lr_from_k_sq`) or the keyword arguments that
+        describe ``G(k^2)`` to the filter kernel (``_native.make_green``: kind, exponent, smearing, prefactor
+        [, table]).  Defaults to the in-kernel potential of :meth:`_native_descriptor`.
+        """
+        descriptor = self._native_descriptor()
+        if descriptor is None:
+            return None
+        smearing, prefactor = self._scalars()
+        return dict(kind=descriptor[0], exponent=descriptor[1], smearing=smearing, prefactor=prefactor)
+
     # -- interface -------------------------------------------------------------------------
     def f_cutoff(self, dist, pair_mask=None):
         if self.exclusion_radius is None:
@@ -327,6 +339,27 @@ class SplinePotential(Potential):
                 torch.as_tensor(self._yhat_at_zero_arg, dtype=zero.dtype, device=zero.device)
             self._splines_for = key
         return self._spline, self._krn_spline
+
+    def _native_filter(self):
+        """G(k^2) = prefactor * spline(k^2) evaluated per k-point inside the filter kernel (green kinds 3 / 4):
+        the knots, values and second derivatives travel as one small float64 table"""
+        _, krn = self._splines()
+        if not self.k_grid.is_cuda:
+            return None
+        key = self._splines_for
+        if getattr(self, "_filter_table_for", None) != key:
+            if self._reciprocal:
+                inv, head = krn._inverse_axis, krn._zero_spline
+                parts = [inv.x_points, inv.y_points, inv.d2y_points, head.x_points, head.y_points, head.d2y_points]
+                n = inv.x_points.shape[0]
+            else:
+                parts = [krn.x_points, krn.y_points, krn.d2y_points]
+                n = krn.x_points.shape[0]
+            self._filter_table = torch.cat([p.detach().to(torch.float64).reshape(-1) for p in parts]).contiguous()
+            self._filter_knots = int(n)
+            self._filter_table_for = key
+        return dict(kind=4 if self._reciprocal else 3, exponent=self._filter_knots, smearing=1.0,
+                    prefactor=self._scalars()[1], table=self._filter_table)
 
     def from_dist(self, dist, pair_mask=None):
         # as in the reference: the prefactor multiplies the (already scaled) long-range part again
