@@ -222,3 +222,18 @@ def test_spline_kernel_evaluated_in_the_filter_kernel(p3m, reciprocal, dtype):
     assert float((got - want.to(dtype)).abs().max() / want.abs().max()) < tol
     mesh = torch.randn((2,) + ns, generator=gen, dtype=torch.float64).to("cuda", dtype)
     assert rel_err(f_gpu(mesh), f_tab(mesh).detach()) < (1e-10 if dtype == torch.float64 else 2e-4)
+
+
+def test_debug_bounds_check_catches_a_bad_pair_list(monkeypatch):
+    """TPME_DEBUG_BOUNDS: out-of-range neighbor indices raise instead of writing out of bounds"""
+    import torchpme_b200 as tp
+    from torchpme_b200 import _native
+
+    pos, q, cell, idx, d = rocksalt(4, dtype=torch.float32, device="cuda", cutoff=5.0)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=1.0).to("cuda"), mesh_spacing=float(cell[0, 0]) / 6)
+    monkeypatch.setattr(_native, "DEBUG_BOUNDS", True)
+    calc(q, cell, pos, idx, d)
+    bad = idx.clone()
+    bad[3, 1] = pos.shape[0]
+    with pytest.raises(IndexError, match="neighbor_indices must lie in"):
+        calc(q, cell, pos, bad, d)

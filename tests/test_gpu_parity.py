@@ -28,9 +28,16 @@ def _norm(ref, natural):
     return max(float(np.abs(ref).max()), 1e-2 * natural)
 
 
-@pytest.fixture(params=["direct", "tiled"])
+def _case_modes(cases):
+    """(case, kernel family) pairs: the tiled kernels cover 4 interpolation nodes, other orders only have the
+    direct ones"""
+    return [pytest.param(c, m, id=f"{c['name']}-{m}") for c in cases
+            for m in (("direct", "tiled") if c["nodes"] == 4 else ("direct",))]
+
+
+@pytest.fixture
 def tile_mode(request, monkeypatch):
-    """run with the direct kernels (interp.cu) and with the tiled ones (tiles.cu) forced on"""
+    """run with the direct kernels (interp.cu) or with the tiled ones (tiles.cu) forced on"""
     from torchpme_b200 import _native
     monkeypatch.setattr(_native, "TILE_MODE", "on" if request.param == "tiled" else "off")
     monkeypatch.setattr(_native, "TILE_SPREAD", "on" if request.param == "tiled" else "auto")
@@ -46,13 +53,10 @@ def _calc(tp, case, dtype, device="cuda"):
 
 @pytest.mark.parametrize("cell_grad", [True, False], ids=["modular", "fused"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+@pytest.mark.parametrize("case, tile_mode", _case_modes(CASES), indirect=["tile_mode"])
 def test_calculator_matches_reference_golden(case, dtype, cell_grad, tile_mode):
     """cell_grad=True exercises the modular autograd nodes + table route, False the fused fast path"""
     import torchpme_b200 as tp
-
-    if tile_mode == "tiled" and case["nodes"] != 4:
-        pytest.skip("the tiled kernels cover 4 interpolation nodes; other orders use the direct kernels")
 
     g = case_arrays(DATA, case["name"])
     dev = "cuda"
@@ -90,14 +94,12 @@ P_CASES, P_DATA = _periodic_cases()
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("case", P_CASES, ids=[c["name"] for c in P_CASES])
+@pytest.mark.parametrize("case, tile_mode", _case_modes(P_CASES), indirect=["tile_mode"])
 def test_two_dimensional_periodicity_matches_reference_golden(case, dtype, tile_mode):
     """`periodic=` with exactly two periodic axes: the slab correction of potentials/coulomb.py:6-40,
     applied at calculators/pme.py:138-140; values and all gradients against the reference"""
     import torchpme_b200 as tp
 
-    if tile_mode == "tiled" and case["nodes"] != 4:
-        pytest.skip("the tiled kernels cover 4 interpolation nodes")
     g = case_arrays(P_DATA, case["name"])
     dev = "cuda"
     q = torch.tensor(g["charges"], dtype=dtype, device=dev, requires_grad=True)

@@ -24,6 +24,9 @@ P3M, LAGRANGE = 0, 1
 METHOD_ID = {"P3M": P3M, "Lagrange": LAGRANGE}
 GREEN_TABLE, GREEN_COULOMB, GREEN_IPL = 0, 1, 2
 
+#: TPME_DEBUG_BOUNDS=1: validate the pair list against the number of atoms before every pair sum (host sync)
+DEBUG_BOUNDS = os.environ.get("TPME_DEBUG_BOUNDS", "0") == "1"
+
 # number of kernel launches issued through this binding (bench.py reports it)
 launch_counter = 0
 
@@ -806,6 +809,12 @@ def pair_forward(charges, idx, dist, pair_values, mask_u8, full_list: bool, pot:
     """accumulates into `out` (allocated and zeroed here when None)"""
     lib = load()
     n, c = charges.shape
+    if DEBUG_BOUNDS and idx.numel():
+        # the kernels trust the pair list (like the reference's index_add_ on CUDA, which device-asserts):
+        # TPME_DEBUG_BOUNDS=1 checks it on the host first (one synchronisation)
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo < 0 or hi >= n:
+            raise IndexError(f"neighbor_indices must lie in [0, {n}), got values in [{lo}, {hi}]")
     if out is None:
         out = torch.zeros_like(charges)
     with _on(charges, "charges"):
