@@ -370,8 +370,12 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
         int gy = gy0 + ry; gy -= gy >= g.ny ? g.ny : 0;
         T* grow = dst + ((int64_t)gx * g.ny + gy) * g.nz;
         const T* srow = tile + rx * g.sx + ry * g.sy;
-        bulk_reduce_add<T>(grow + z_lo, srow, main_bytes);
-        bulk_reduce_add<T>(grow + z_hi, srow + g.tz, halo_bytes);
+        if (z_hi != 0) {        // the halo continues the row in the mesh as it does in the tile: one reduction
+          bulk_reduce_add<T>(grow + z_lo, srow, main_bytes + halo_bytes);
+        } else {                // last z tile: the halo wraps to z = 0
+          bulk_reduce_add<T>(grow + z_lo, srow, main_bytes);
+          bulk_reduce_add<T>(grow, srow + g.tz, halo_bytes);
+        }
       }
       bulk_commit();
       bulk_wait_read_all();   // the tile is re-zeroed (next channel) / freed (exit) only after the reads
@@ -432,8 +436,12 @@ tile_gather4_kernel(const T* __restrict__ mesh, const T* __restrict__ sorted_rec
         int gy = gy0 + ry; gy -= gy >= g.ny ? g.ny : 0;
         const T* grow = src + ((int64_t)gx * g.ny + gy) * g.nz;
         T* srow = tile + rx * g.sx + ry * g.sy;
-        bulk_load(srow, grow + z_lo, main_bytes, bar);            // the tile's own z range ...
-        bulk_load(srow + g.tz, grow + z_hi, halo_bytes, bar);     // ... and the halo behind it (next tile / wrap)
+        if (z_hi != 0) {        // the tile's own z range and the halo behind it are contiguous in the mesh
+          bulk_load(srow, grow + z_lo, main_bytes + halo_bytes, bar);
+        } else {                // last z tile: the halo wraps to z = 0
+          bulk_load(srow, grow + z_lo, main_bytes, bar);
+          bulk_load(srow + g.tz, grow, halo_bytes, bar);
+        }
       }
     }
     // first atom of this thread: its record travels while the tile is still arriving
