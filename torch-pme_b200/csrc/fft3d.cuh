@@ -1236,7 +1236,7 @@ int dispatch_plane(int ny, int nz, bool forward, const void* in, void* out, int 
 template <typename GT>
 int green_variant(const GreenDev<GT>& g) {
   const bool coulomb_form = (g.kind == 1) || (g.kind == 2 && g.exponent == 1);
-  if (!coulomb_form || (g.p3m_nodes > 0 && g.p3m_mode != 0)) return GV_GENERIC;
+  if (!coulomb_form) return GV_GENERIC;
   const bool ortho = g.recip[1] == 0 && g.recip[2] == 0 && g.recip[3] == 0 && g.recip[5] == 0 &&
                      g.recip[6] == 0 && g.recip[7] == 0;
   if (ortho) return GV_ORTHO;

@@ -126,8 +126,11 @@ struct GreenDev {
   const void* table;
 };
 
-// scale * G(k) at integer mesh frequency (ix, iy, iz) of the rFFT layout
-template <typename T, typename S>
+// scale * G(k) at integer mesh frequency (ix, iy, iz) of the rFFT layout.  EXT compiles the extended kinds in
+// (spline kernels, P3M influence modes 1..3): the stand-alone table / multiply kernels do, the fused x pass of
+// the hand-written FFT does not (its register budget is tuned for the closed forms; extended kinds reach it
+// as a table written by tpme_green_table, see is_extended_green).
+template <typename T, typename S, bool EXT = false>
 __device__ __forceinline__ T green_value(const GreenDev<T>& g, int ix, int iy, int iz, int nx,
                                          int ny, int nz, int64_t flat) {
   using M = MathFn<T>;
@@ -141,7 +144,7 @@ __device__ __forceinline__ T green_value(const GreenDev<T>& g, int ix, int iy, i
   const T kz = fx * g.recip[2] + fy * g.recip[5] + fz * g.recip[8];
   const T k_sq = kx * kx + ky * ky + kz * kz;
   T val;
-  if (g.kind >= 3) {
+  if (EXT && g.kind >= 3) {
     // tabulated kernel: cubic spline in k^2 (double arithmetic, the tables are double)
     val = g.amplitude * (T)spline_kernel_dev(g.kind, reinterpret_cast<const double*>(g.table), g.exponent, (double)k_sq);
   } else if (k_sq == T(0)) {
@@ -163,7 +166,7 @@ __device__ __forceinline__ T green_value(const GreenDev<T>& g, int ix, int iy, i
     T u2 = T(1);
     const T s2 = s * s;
     for (int i = 0; i < g.p3m_nodes; ++i) u2 *= s2;
-    if (g.p3m_mode == 0) {
+    if (!EXT || g.p3m_mode == 0) {
       val = (u2 == T(0)) ? T(0) : val / u2;
     } else {
       // (k . D)^mode / (U^2 |D|^(4 mode)),  D_a = sum_i c_i / (i + 1) sin((i + 1) k_a h_a) / h_a
@@ -219,6 +222,11 @@ inline GreenDev<T> make_green(const tpme_green* h) {
   g.amplitude = (T)amp;
   g.k0_value = (T)k0;
   return g;
+}
+
+// kinds that only the EXT instantiation of green_value evaluates
+inline bool is_extended_green(const tpme_green* g) {
+  return g->kind >= 3 || (g->p3m_nodes > 0 && (g->p3m_mode & 255) != 0);
 }
 
 inline int check_green(const tpme_green* g) {

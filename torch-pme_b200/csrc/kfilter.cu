@@ -34,7 +34,7 @@ green_multiply_kernel(S* __restrict__ hat, int n_channels, int nx, int ny, int n
     const int64_t t = i / nzh;
     const int iy = (int)(t % ny);
     const int ix = (int)(t / ny);
-    const S gv = (S)green_value<T, S>(g, ix, iy, iz, nx, ny, nz, i);
+    const S gv = (S)green_value<T, S, true>(g, ix, iy, iz, nx, ny, nz, i);
     for (int c = 0; c < n_channels; ++c) {
       S* p = hat + 2 * (c * total + i);
       if (i == 0 && dc_out != nullptr) dc_out[c] = p[0];
@@ -60,7 +60,7 @@ green_table_kernel(S* __restrict__ out, int nx, int ny, int nz, GreenDev<T> g) {
        i += (int64_t)gridDim.x * blockDim.x) {
     const int iz = (int)(i % nzh);
     const int64_t t = i / nzh;
-    out[i] = (S)green_value<T, S>(g, (int)(t / ny), (int)(t % ny), iz, nx, ny, nz, i);
+    out[i] = (S)green_value<T, S, true>(g, (int)(t / ny), (int)(t % ny), iz, nx, ny, nz, i);
   }
 }
 
@@ -245,6 +245,8 @@ extern "C" int tpme_kfilter_apply(tpme_fft_plan plan, const void* mesh_in, void*
   TPME_REQUIRE(plan != nullptr, "null plan");
   if (plan->own_fft && keep_hat == nullptr) {
     if (int rc = check_green(green)) return rc;
+    TPME_REQUIRE(!is_extended_green(green),
+                 "spline kernels and P3M modes 1-3 reach the fused FFT as a table: tpme_green_table, then kind 0");
     cudaStream_t s = (cudaStream_t)stream;
     if (plan->dtype == 1)
       return filter_pow2_f64(mesh_in, mesh_out, work_hat, plan->batch, plan->nx, plan->ny, plan->nz,

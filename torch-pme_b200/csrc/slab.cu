@@ -251,6 +251,7 @@ extern "C" int tpme_slab_fft_x_green_push(int dtype, int n_channels, int nx, int
   TPME_REQUIRE(pow2_dim(nx), "the slab-decomposed FFT needs power-of-two mesh dimensions in 8..512");
   if (int rc = check_peers(peers, nx, ny)) return rc;
   if (int rc = check_green(green)) return rc;
+  TPME_REQUIRE(!is_extended_green(green), "the slab x pass evaluates closed-form kernels and tables only");
   if (n_channels <= 0) return 0;
   const int w = peers->n_ranks, rank = peers->rank;
   const int nxl = nx / w, nyl = ny / w, nzh = nz / 2 + 1;
@@ -283,6 +284,7 @@ extern "C" int tpme_slab_fft_x_green(int dtype, void* mesh_hat_t, int n_channels
   TPME_REQUIRE(pow2_dim(nx), "the slab-decomposed FFT needs power-of-two mesh dimensions in 8..512");
   TPME_REQUIRE(y0 >= 0 && ny_local > 0 && y0 + ny_local <= ny, "y slab must lie inside [0, ny)");
   if (int rc = check_green(green)) return rc;
+  TPME_REQUIRE(!is_extended_green(green), "the slab x pass evaluates closed-form kernels and tables only");
   if (n_channels <= 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == 1)

@@ -553,6 +553,17 @@ def kfilter_apply(mesh, green: _Green, keep_hat=False, want_dc=False):
     work = torch.empty(half_complex_shape(mesh.shape), dtype=mesh.dtype, device=mesh.device)
     kept = torch.empty_like(work) if keep_hat else None
     dc = torch.empty(c, dtype=mesh.dtype, device=mesh.device) if want_dc else None
+    if plan.own_fft and not keep_hat and (green.kind >= 3 or (green.p3m_nodes > 0 and green.p3m_mode & 255)):
+        # spline kernels / P3M modes 1-3: the table kernel evaluates them per k-point (tpme_green_table), the
+        # fused x pass of the hand-written FFT multiplies by that table (its register budget is tuned for the
+        # closed forms)
+        table = green_table(mesh.dtype, (nx, ny, nz), green, mesh.device)
+        lean = _Green()
+        lean.kind, lean.scale, lean.table = GREEN_TABLE, 1.0, table.data_ptr()
+        for k in range(9):
+            lean.recip[k] = green.recip[k]
+        lean._keepalive = table
+        green = lean
     with _on(mesh, "mesh"):
         _check(lib.tpme_kfilter_apply(plan.handle, _dev(mesh, "mesh_values"), _dev(out, "out"),
                                       _dev(work, "work"), _dev(kept, "keep"), ctypes.byref(green),
