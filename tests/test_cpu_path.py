@@ -144,3 +144,31 @@ def test_torch_compile_on_cpu():
     assert type(out) is torch.Tensor and torch.allclose(out, ref, atol=1e-12)
     out.sum().backward()
     assert torch.isfinite(p.grad).all()
+
+
+def test_forward_from_pairs_on_cpu_is_the_composition():
+    """pair list as indices + image shifts on CPU tensors: distances_from + forward, gradients through both"""
+    import torchpme_b200 as tp
+    from oracle import pme_oracle as oracle
+    from torchpme_b200.neighbors import distances_from
+
+    rng = np.random.default_rng(0)
+    cell_np = np.array([[6.0, 0.0, 0.0], [0.8, 5.5, 0.0], [-0.4, 0.6, 6.2]])
+    pos_np = rng.uniform(0, 1, (24, 3)) @ cell_np
+    idx_np, d_np, s_np = oracle.neighbor_list(pos_np, cell_np, 3.0)
+    q = torch.tensor(rng.normal(size=(24, 1)))
+    cell = torch.tensor(cell_np)
+    idx, shifts = torch.tensor(idx_np), torch.tensor(s_np, dtype=torch.int32)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=0.8), mesh_spacing=0.4)
+    p0 = torch.tensor(pos_np, requires_grad=True)
+    d = distances_from(p0, cell, idx, shifts)
+    np.testing.assert_allclose(d.detach().numpy(), d_np, rtol=1e-12)
+    V0 = calc(q, cell, p0, idx, d)
+    (g0,) = torch.autograd.grad((V0 * q).sum(), p0)
+    p1 = torch.tensor(pos_np, requires_grad=True)
+    V1 = calc.forward_from_pairs(q, cell, p1, idx, shifts)
+    (g1,) = torch.autograd.grad((V1 * q).sum(), p1)
+    np.testing.assert_allclose(V1.detach().numpy(), V0.detach().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(g1.numpy(), g0.numpy(), rtol=1e-10, atol=1e-12)
+    # the complete force (mesh + real space) sums to ~0 over the atoms (up to the mesh discretisation error)
+    assert float(g1.sum(0).abs().max()) < 1e-2 * float(g1.abs().max())

@@ -253,3 +253,51 @@ def test_forward_from_pairs_equals_the_composition(calc_name, dtype):
     q1 = q.clone().requires_grad_(True)
     (gq1,) = torch.autograd.grad(calc.forward_from_pairs(q1, cell, pos, idx, s), q1, grad_outputs=w)
     assert rel_err(gq1, gq0) < tol
+
+
+@pytest.mark.parametrize("full", [False, True], ids=["half", "full"])
+@pytest.mark.parametrize("index_dtype", [torch.int64, torch.int32])
+def test_crowded_atoms_take_the_second_search(full, index_dtype):
+    """more partners per atom than the shared-memory hit list holds (32): the rest is written by a second walk;
+    dense system, ~100 (half: ~50) neighbors per atom, triclinic cell, against the brute-force oracle"""
+    from torchpme_b200.neighbors import DeviceNeighborList, neighbor_list
+
+    rng = np.random.default_rng(5)
+    cell = np.array([[8.0, 0.0, 0.0], [1.5, 7.5, 0.0], [-1.0, 0.8, 8.5]])
+    pos = rng.uniform(0, 1, (200, 3)) @ cell
+    cutoff = 4.0
+    idx, d, s = neighbor_list(torch.tensor(pos, device="cuda"), torch.tensor(cell, device="cuda"), cutoff,
+                              full_neighbor_list=full, index_dtype=index_dtype)
+    o_idx, o_d, o_s = oracle.neighbor_list(pos, cell, cutoff, full=full)
+    assert idx.shape[0] == o_idx.shape[0] and idx.shape[0] / 200 > (64 if full else 32)
+    if full:
+        got = np.concatenate([idx.cpu().numpy().astype(np.int64), s.cpu().numpy()], axis=1)
+        want = np.concatenate([o_idx, o_s], axis=1)
+        assert np.array_equal(got[np.lexsort(got.T[::-1])], want[np.lexsort(want.T[::-1])])
+    else:
+        rows, dist = _canonical(idx.cpu().numpy(), d.cpu().numpy(), s.cpu().numpy())
+        o_rows, o_dist = _canonical(o_idx, o_d, o_s)
+        assert np.array_equal(rows, o_rows) and np.abs(dist - o_dist).max() < 1e-12
+    # a capacity that ends in the middle of a CTA's range: the pairs that fit are valid pairs, the count is complete
+    cap = idx.shape[0] // 3
+    nl = DeviceNeighborList(200, torch.tensor(cell, device="cuda"), cutoff, capacity=cap, dtype=torch.float64,
+                            full_neighbor_list=full, index_dtype=index_dtype)
+    ci, cd, cs = nl.build(torch.tensor(pos, device="cuda"))
+    assert nl.overflowed() and int(nl.n_pairs) == idx.shape[0]
+    key = lambda i, sh: set(map(tuple, np.concatenate([i.cpu().numpy().astype(np.int64), sh.cpu().numpy()], axis=1)))  # noqa: E731
+    assert key(ci, cs) <= key(idx, s) and len(key(ci, cs)) == cap
+
+
+def test_empty_and_tiny_systems():
+    from torchpme_b200.neighbors import neighbor_list
+
+    cell = torch.eye(3, dtype=torch.float64, device="cuda") * 5.0
+    idx, d, s = neighbor_list(torch.empty((0, 3), dtype=torch.float64, device="cuda"), cell, 2.0)
+    assert idx.shape == (0, 2) and d.shape == (0,) and s.shape == (0, 3)
+    one = torch.tensor([[0.3, 0.4, 0.5]], dtype=torch.float64, device="cuda")
+    idx, d, s = neighbor_list(one, cell, 2.0)                     # no image within the cutoff
+    assert idx.shape[0] == 0
+    idx, d, s = neighbor_list(one, cell, 5.5)                     # the six nearest self images: three in a half list
+    assert idx.shape[0] == 3 and bool((idx == 0).all()) and torch.allclose(d, torch.full_like(d, 5.0))
+    idx, d, s = neighbor_list(one, cell, 5.5, full_neighbor_list=True)
+    assert idx.shape[0] == 6
