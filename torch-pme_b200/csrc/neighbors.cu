@@ -4,9 +4,9 @@
 //
 //   tpme_nl_sort    wrap + bin the atoms, counting sort by bin (count -> single-pass scan -> place)
 //   tpme_nl_pairs   one thread per sorted atom walks the neighbouring bins ONCE: the partners it finds
-//                   are parked in shared memory, the CTA reserves a contiguous range of the output with
-//                   one atomic on the pair counter, and every thread then writes (i, j), |r_ij| and the
-//                   image shift S of its pairs.  The pair count stays on the device (no host
+//                   are parked in shared memory, every warp reserves a contiguous range of the output with
+//                   one atomic on the pair counter and then writes (i, j), |r_ij| and the image shift S of
+//                   its pairs, neighbouring lanes storing neighbouring pairs.  The pair count stays on the device (no host
 //                   synchronisation is needed to go on); pairs beyond `capacity` are dropped (the
 //                   caller compares the count with the capacity) -- so a step with a fixed-capacity
 //                   list is one CUDA graph.  Half lists visit half of the bins (neighbors_core.h).
@@ -88,11 +88,8 @@ nl_pairs_kernel(const NlRecord<T>* __restrict__ sorted, const NlShift* __restric
                 I* __restrict__ indices, T* __restrict__ distances, int* __restrict__ shifts,
                 unsigned long long* __restrict__ n_pairs) {
   __shared__ uint2 hits[FILL ? kNlHits * kNlThreads : 1];
-  __shared__ int warp_total[kNlThreads / 32];
-  __shared__ int first[FILL ? kNlThreads : 1];
-  __shared__ unsigned long long block_base;
   const int64_t slot = (int64_t)blockIdx.x * kNlThreads + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   int found = 0;
   if (slot < n) {
     if (FILL) {
@@ -103,42 +100,41 @@ nl_pairs_kernel(const NlRecord<T>* __restrict__ sorted, const NlShift* __restric
       found = nl_visit_slot<T>(slot, sorted, sshift, bin_start, g, cnt);
     }
   }
-  // exclusive scan of the counts over the CTA, one atomic to reserve the CTA's output range
+  // Every WARP reserves its own range of the output (prefix sums of the counts by shuffles, one atomic on the
+  // pair counter): no CTA barrier, so a warp whose atoms had few partners does not wait for the others.
   int incl = found;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     const int y = __shfl_up_sync(0xffffffffu, incl, off);
     if (lane >= off) incl += y;
   }
-  if (lane == 31) warp_total[warp] = incl;
-  __syncthreads();
-  int before = 0, total = 0;
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  unsigned long long reserved = 0;
+  if (lane == 0) reserved = atomicAdd(n_pairs, (unsigned long long)total);
+  const int64_t base = (int64_t)__shfl_sync(0xffffffffu, reserved, 0);
+  if (!FILL) return;
+  const int local = incl - found;                      // first pair of this lane inside the warp's range
+  __syncwarp();                                        // the hit lists of the warp are complete
+  // Write-out, coalesced: pair p of the warp's range is written by lane p mod 32 -- its owner (the lane that
+  // found it) is looked up in the prefix sums, its partner in the owner's hit list -- so that neighbouring
+  // lanes store neighbouring pairs (one thread writing its own run would touch 32 sectors per store).
+  const int64_t slot0 = slot - lane;
+  const int tid0 = threadIdx.x - lane;
+  for (int p0 = 0; p0 < total; p0 += 32) {
+    const int p = p0 + lane;
+    int lo = 0, hi = 31;                               // last lane whose first pair is <= p
 #pragma unroll
-  for (int w = 0; w < kNlThreads / 32; ++w) {
-    if (w < warp) before += warp_total[w];
-    total += warp_total[w];
-  }
-  if (threadIdx.x == 0) block_base = total > 0 ? atomicAdd(n_pairs, (unsigned long long)total) : 0ull;
-  const int local = before + (incl - found);          // first pair of this thread inside the CTA's range
-  if (FILL) first[threadIdx.x] = local;
-  __syncthreads();
-  if (!FILL || total == 0) return;
-  // Write-out, coalesced: pair p of the CTA's range is written by thread p mod 128 -- its owner (the thread
-  // that found it) is looked up in the prefix sums, its partner in the owner's hit list -- so that
-  // neighbouring lanes store neighbouring pairs (one thread writing its own run would touch 32 sectors
-  // per store instruction).
-  const int64_t base = (int64_t)block_base;
-  const int64_t slot0 = (int64_t)blockIdx.x * kNlThreads;
-  for (int p = threadIdx.x; p < total; p += kNlThreads) {
-    int lo = 0, hi = kNlThreads - 1;                   // last thread whose first pair is <= p
-    while (lo < hi) {
+    for (int step = 0; step < 5; ++step) {
       const int mid = (lo + hi + 1) >> 1;
-      if (first[mid] <= p) lo = mid; else hi = mid - 1;
+      const int first_mid = __shfl_sync(0xffffffffu, local, mid);
+      if (first_mid <= p) lo = mid; else hi = mid - 1;
     }
-    const int k = p - first[lo];
-    if (k >= kNlHits || base + p >= capacity) continue;   // beyond the parked ones: written by the owner below
-    const uint2 h = hits[k * kNlThreads + lo];
-    nl_emit<T, I>(slot0 + lo, (int)h.x, h.y, sorted, sshift, g, base + p, indices, distances, shifts);
+    const int k = p - __shfl_sync(0xffffffffu, local, lo);
+    if (p < total && k < kNlHits && base + p < capacity) {   // beyond the parked ones: written by the owner below
+      const uint2 h = hits[k * kNlThreads + tid0 + lo];
+      nl_emit<T, I>(slot0 + lo, (int)h.x, h.y, sorted, sshift, g, base + p, indices, distances, shifts);
+    }
   }
   if (found > kNlHits) {                                // crowded atom: search again for the rest
     HitWriter<T, I> w{slot, base + local, capacity, sorted, sshift, &g, indices, distances, shifts, 0};

@@ -166,12 +166,20 @@ TPME_HD int nl_visit_slot(int64_t slot, const NlRecord<T>* __restrict__ sorted, 
         const int s_end = bin_start[column + wz1 + 1];
         int s = bin_start[column + wz0];
         if (own_bin) s = (int)slot + 1;
-        for (; s < s_end; ++s) {
-          if (full && zero_shift && s == slot) continue;
-          const T r2 = nl_dist_sq<T>(me, sorted[s], g, sx, sy, sz);
-          if (!(r2 < cutoff_sq)) continue;
-          hit(s, image);
-          ++found;
+        // four candidates are loaded before the first one is tested (independent loads in flight)
+        for (; s < s_end; s += 4) {
+          NlRecord<T> cand[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cand[k] = sorted[s + k < s_end ? s + k : s_end - 1];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (s + k >= s_end) break;
+            if (full && zero_shift && s + k == slot) continue;
+            const T r2 = nl_dist_sq<T>(me, cand[k], g, sx, sy, sz);
+            if (!(r2 < cutoff_sq)) continue;
+            hit(s + k, image);
+            ++found;
+          }
         }
       }
     }
