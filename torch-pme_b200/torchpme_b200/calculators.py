@@ -96,7 +96,7 @@ def _side_stream(device) -> "torch.cuda.Stream":
 class _FusedStepConfig:
     """by-value launch parameters of one fused PME / P3M evaluation"""
     __slots__ = ("r2u", "ns", "nodes", "method", "green_args", "pair_pot", "full_list",
-                 "half_ivolume", "self_half", "background_ivolume")
+                 "half_ivolume", "self_half", "background_ivolume", "defer_join")
 
 
 class _FusedMeshPotential(torch.autograd.Function):
@@ -132,21 +132,35 @@ class _FusedMeshPotential(torch.autograd.Function):
         need_dist = d is None
         if need_dist:       # allocated on the main stream like `out`: both branches join before anything is freed
             d = torch.zeros(idx.shape[0], dtype=q.dtype, device=q.device)
+        # defer_join (set by GraphedStep for its private graph only): the two branches never join inside this
+        # node -- the pair sum goes to its own buffer and is added to the mesh result ON THE SIDE STREAM, so the
+        # mesh pipeline (forward and backward) does not wait for a pair list that is still crossing PCIe.  The
+        # returned potentials (and dL/dd in backward) are then complete on the side stream only; the caller joins.
+        defer = bool(cfg.defer_join) and not ctx.needs_input_grad[0]
+        ctx.defer = defer
+        pair_out = torch.empty_like(q) if defer else out
         with torch.cuda.stream(side):
-            out.zero_()
+            pair_out.zero_()
             if need_dist:
                 _native.pair_distances(pos, cell_host, idx, shifts, _native.pair_count_of(idx), d)
-            _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
+            _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=pair_out)
+        if defer:
+            out.zero_()
         # atoms binned by mesh tile once per step: the spread, the gather and both backward launches
         # stage their pencil of the mesh in shared memory (csrc/tiles.cu); None = direct kernels
         tiles = _native.tile_sort(pos, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
         rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
         green = _native.make_green(scale=1.0, **cfg.green_args)
         phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
-        main.wait_stream(side)
+        if not defer:
+            main.wait_stream(side)
         epi = _native.make_epilogue(q, dc, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume)
         _, dvalues = _native.gather(phi, pos, cfg.r2u, cfg.nodes, cfg.method, want_grad=need_pos,
                                     values_out=out, epilogue=epi, tiles=tiles)
+        if defer:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out.add_(pair_out)
         ctx.cfg, ctx.tiles = cfg, tiles
         ctx.save_for_backward(q, pos, d, idx, mask_u8, dvalues)
         return out
@@ -202,10 +216,12 @@ class _FusedMeshPotential(torch.autograd.Function):
             else:
                 _native.gather(psi, pos, cfg.r2u, cfg.nodes, cfg.method, values_out=g_q, epilogue=epi,
                                tiles=tiles)
-        if forked:
+        if forked and not (ctx.defer and not need_q):
             main.wait_stream(side)
         if shifts is not None:
             if need_d:
+                if ctx.defer and forked and not need_q:
+                    main.wait_stream(side)      # the real-space forces are added to the mesh forces here
                 g_pos = g_pos4[:, :3] if g_pos is None else g_pos + g_pos4[:, :3]
             g_d = None
         return g_q, g_pos, g_d, None, None, None, None, None
@@ -371,11 +387,13 @@ class PMECalculator(Calculator):
         ns = geom.ns_mesh(self.mesh_spacing)
         kind, exponent = pot._native_descriptor()
         smearing, prefactor = pot._scalars()
+        defer_join = bool(getattr(self, "_defer_join", False))
         key = (id(geom), ns, kind, exponent, smearing, prefactor, pot.exclusion_radius,
-               pot.exclusion_degree, self.full_neighbor_list)
+               pot.exclusion_degree, self.full_neighbor_list, defer_join)
         cfg = self._fused_cfg if self._fused_key == key else None
         if cfg is None:
             cfg = _FusedStepConfig()
+            cfg.defer_join = defer_join
             cfg.r2u, cfg.ns = geom.r2u(ns), ns
             cfg.nodes, cfg.method = self.interpolation_nodes, _native.METHOD_ID[self._method]
             cfg.green_args = dict(kind=kind, exponent=exponent, smearing=smearing, prefactor=prefactor,

@@ -60,16 +60,33 @@ class GraphedStep:
                     "energy": torch.empty((), dtype=positions.dtype).pin_memory(),
                     "grad_positions": torch.empty(positions.shape, dtype=positions.dtype).pin_memory(),
                 }
-            for _ in range(max(1, warmup)):
-                self._step()
-            self.stream.synchronize()
-            with torch.cuda.graph(self.graph, stream=self.stream):
-                if host_io:
-                    self._copy_in()
-                self.energy, self.grad_positions, self.grad_distances = self._step()
-                if host_io:
-                    self.host["grad_positions"].copy_(self.grad_positions, non_blocking=True)
-                    self.host["energy"].copy_(self.energy, non_blocking=True)
+            # Inside this private graph the two branches of the calculator node need not join where the node
+            # ends (calculators._FusedMeshPotential, defer_join): the mesh pipeline -- forward AND backward,
+            # the latter only needs dE/dV = q -- and the D2H copy of the forces run while the pair list is
+            # still crossing PCIe; what depends on the list (pair sum, energy, dE/dd) follows on the side
+            # stream and everything joins once, at the end of the graph.
+            defer = host_io and not fused_energy_gradients and hasattr(calculator, "_fused_config")
+            self._deferred = defer
+            had = getattr(calculator, "_defer_join", False)
+            if defer:
+                calculator._defer_join = True
+            try:
+                for _ in range(max(1, warmup)):
+                    self._step(defer)
+                    self._join()
+                self.stream.synchronize()
+                with torch.cuda.graph(self.graph, stream=self.stream):
+                    if host_io:
+                        self._copy_in()
+                    self.energy, self.grad_positions, self.grad_distances = self._step(defer)
+                    if host_io:     # the forces are complete on this stream: their copy need not wait for the join
+                        self.host["grad_positions"].copy_(self.grad_positions, non_blocking=True)
+                    self._join()
+                    if host_io:
+                        self.host["energy"].copy_(self.energy, non_blocking=True)
+            finally:
+                if defer:
+                    calculator._defer_join = had
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         torch.cuda.synchronize(dev)
         set_nan_check(nan_check_before)
@@ -97,7 +114,20 @@ class GraphedStep:
         # the calculator forks the real-space kernels onto `side` (ordered after the copies above)
         # and joins before it needs them; every other consumer of the pair list sits behind that join
 
-    def _step(self):
+    def _join(self):
+        """the capture stream waits for the energy branch and for the real-space branch of the calculator"""
+        from .calculators import _side_stream
+
+        if self.fused_energy_gradients:      # energy_and_gradients joins its own branches; `aux` is unused
+            return
+        main = torch.cuda.current_stream(self.positions.device)
+        main.wait_stream(self.aux)
+        if self._deferred:
+            main.wait_stream(_side_stream(self.positions.device))
+
+    def _step(self, defer: bool = False):
+        from .calculators import _side_stream
+
         if self.fused_energy_gradients:
             energy, g_pos, g_d, _ = self.calculator.energy_and_gradients(
                 self.charges, self.cell, self.positions, self.neighbor_indices, self.neighbor_distances)
@@ -108,13 +138,13 @@ class GraphedStep:
         # directly with dE/dV = q (a vector-Jacobian product) instead of going through the tape of
         # the multiply + sum -- same numbers, three small kernels fewer on the critical path
         main = torch.cuda.current_stream(self.positions.device)
-        self.aux.wait_stream(main)
+        # with deferred joins V is complete on the calculator's side stream, not here
+        self.aux.wait_stream(_side_stream(self.positions.device) if defer else main)
         with torch.cuda.stream(self.aux):
             energy = (V.detach() * self.charges).sum()
         g_pos, g_d = torch.autograd.grad(V, (self.positions, self.neighbor_distances),
                                          grad_outputs=self.charges)
-        main.wait_stream(self.aux)
-        return energy, g_pos, g_d
+        return energy, g_pos, g_d    # the caller joins (self._join)
 
     def replay(self) -> None:
         self.graph.replay()
