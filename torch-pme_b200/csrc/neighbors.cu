@@ -281,13 +281,14 @@ extern "C" int tpme_nl_sort(int dtype, const void* positions, int64_t n_atoms,
   int* bin_count = scratch;
   void* scan_state = scratch + ((bins + 3) & ~3ll);
   int2* key_rank = reinterpret_cast<int2*>(scratch + ((bins + 3) & ~3ll) + 2 * ((scan_state_words(bins) + 1) & ~1ll));
-  TPME_CUDA_OK(cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)bins, s));
+  // counters + scan scratch behind them: one memset
+  TPME_CUDA_OK(cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)(((bins + 3) & ~3ll) + 2 * ((scan_state_words(bins) + 1) & ~1ll)), s));
   const unsigned grid = (unsigned)((n_atoms + 255) / 256);
   if (n_atoms > 0) {
     if (dtype == 0) nl_bin_kernel<float><<<grid, 256, 0, s>>>((const float*)positions, n_atoms, g, bin_count, key_rank);
     else nl_bin_kernel<double><<<grid, 256, 0, s>>>((const double*)positions, n_atoms, g, bin_count, key_rank);
   }
-  TPME_CUDA_OK(launch_exclusive_scan<int>(bin_count, bin_start, bins, scan_state, s));
+  TPME_CUDA_OK(launch_exclusive_scan<int>(bin_count, bin_start, bins, scan_state, s, true));
   if (n_atoms > 0) {
     if (dtype == 0)
       nl_place_kernel<float><<<grid, 256, 0, s>>>((const float*)positions, n_atoms, g, bin_start, key_rank,

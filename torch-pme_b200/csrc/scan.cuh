@@ -100,11 +100,15 @@ exclusive_scan_kernel(const int* __restrict__ in, OutT* __restrict__ out, int64_
 }
 
 // out[0 .. n] = exclusive prefix sums of in[0 .. n-1] (out[n] = total)
+// `state_is_zero`: the caller has zeroed the scratch already (e.g. together with the counters, one memset)
 template <typename OutT>
-inline cudaError_t launch_exclusive_scan(const int* in, OutT* out, int64_t n, void* state, cudaStream_t s) {
+inline cudaError_t launch_exclusive_scan(const int* in, OutT* out, int64_t n, void* state, cudaStream_t s,
+                                         bool state_is_zero = false) {
   if (n <= 0) return cudaMemsetAsync(out, 0, sizeof(OutT), s);
-  cudaError_t err = cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (size_t)scan_state_words(n), s);
-  if (err != cudaSuccess) return err;
+  if (!state_is_zero) {
+    cudaError_t err = cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (size_t)scan_state_words(n), s);
+    if (err != cudaSuccess) return err;
+  }
   exclusive_scan_kernel<OutT><<<(unsigned)scan_tiles(n), kScanThreads, 0, s>>>(in, out, n, (unsigned long long*)state);
   return cudaGetLastError();
 }

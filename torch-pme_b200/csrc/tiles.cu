@@ -726,9 +726,9 @@ extern "C" int tpme_tile_sort(int dtype, const tpme_tile_plan* plan, const void*
   cudaStream_t s = (cudaStream_t)stream;
   const TileGeom g = geom_of(*plan, plan->nzt);
   TPME_REQUIRE(((uintptr_t)bin_count % 8) == 0, "workspace alignment");
-  TPME_CUDA_OK(cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)plan->n_bins, s));
-  // scratch of the scan: behind the counters, 8-byte aligned (tpme_tile_bin_count_ints)
+  // the counters and, behind them (8-byte aligned, tpme_tile_bin_count_ints), the scratch of the scan: one memset
   void* scan_state = bin_count + ((plan->n_bins + 1) & ~1);
+  TPME_CUDA_OK(cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)tpme_tile_bin_count_ints(plan), s));
   const unsigned grid = (unsigned)((n_points + 255) / 256);
   if (n_points > 0) {
     if (dtype == 0)
@@ -738,7 +738,7 @@ extern "C" int tpme_tile_sort(int dtype, const tpme_tile_plan* plan, const void*
       tile_count_kernel<double><<<grid, 256, 0, s>>>((const double*)positions, n_points, load_mat3<double>(r2u_host),
                                                      make_dims<double>(g.nx, g.ny, g.nz), g, bin_count, (int2*)key_rank);
   }
-  TPME_CUDA_OK(launch_exclusive_scan<int>(bin_count, bin_start, plan->n_bins, scan_state, s));
+  TPME_CUDA_OK(launch_exclusive_scan<int>(bin_count, bin_start, plan->n_bins, scan_state, s, true));
   if (n_points > 0) {
     if (dtype == 0)
       tile_fill_kernel<float><<<grid, 256, 0, s>>>((const float*)positions, n_points, load_mat3<float>(r2u_host),
