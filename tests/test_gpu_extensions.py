@@ -237,3 +237,22 @@ def test_debug_bounds_check_catches_a_bad_pair_list(monkeypatch):
     bad[3, 1] = pos.shape[0]
     with pytest.raises(IndexError, match="neighbor_indices must lie in"):
         calc(q, cell, pos, bad, d)
+
+
+def test_nan_guard_on_the_fused_path():
+    """the reference raises on NaNs in the filtered mesh (lib/kspace_filter.py:189-195): the fused calculator
+    node does too, unless the guard is switched off"""
+    import torchpme_b200 as tp
+
+    pos, q, cell, idx, d = rocksalt(4, dtype=torch.float32, device="cuda", cutoff=5.0)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=1.0).to("cuda"), mesh_spacing=float(cell[0, 0]) / 6)
+    bad = q.clone()
+    bad[3, 0] = float("nan")
+    tp.set_nan_check(True)
+    with pytest.raises(ValueError, match="NaNs detected in the k-space filter result"):
+        calc(bad, cell, pos, idx, d)
+    tp.set_nan_check(False)
+    try:
+        assert torch.isnan(calc(bad, cell, pos, idx, d)).any()
+    finally:
+        tp.set_nan_check(True)

@@ -17,7 +17,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _cpu, _native
 from ._checks import validate_parameters
-from .mesh import KSpaceFilter, MeshInterpolator, P3MKSpaceFilter, geometry_of
+from .mesh import KSpaceFilter, MeshInterpolator, P3MKSpaceFilter, check_filter_result, geometry_of
 from .potentials import Potential
 
 
@@ -152,6 +152,7 @@ class _FusedMeshPotential(torch.autograd.Function):
         rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
         green = _native.make_green(scale=1.0, **cfg.green_args)
         phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
+        check_filter_result(phi)      # the reference's NaN guard (a host sync; see mesh.set_nan_check)
         if not defer:
             main.wait_stream(side)
         epi = _native.make_epilogue(q, dc, cfg.half_ivolume, cfg.self_half, cfg.background_ivolume)

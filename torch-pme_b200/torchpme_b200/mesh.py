@@ -470,6 +470,20 @@ def set_nan_check(enabled: bool) -> None:
     _nan_check = bool(enabled)
 
 
+def check_filter_result(result: torch.Tensor) -> None:
+    """the reference's guard on the filtered mesh (lib/kspace_filter.py:189-195), same text; one host sync;
+    skipped when switched off (:func:`set_nan_check`) and while a CUDA graph is being captured"""
+    if not _nan_check or (result.is_cuda and torch.cuda.is_current_stream_capturing()):
+        return
+    if torch.isnan(result).any():
+        raise ValueError(
+            "NaNs detected in the k-space filter result. This are probably caused "
+            "by an unsuitable `mesh_spacing`, resulting in a problematic grid of "
+            f"shape: {list(result.shape)}. Try adjsuting the grid by using a "
+            "different `mesh_spacing` value."
+        )
+
+
 class KSpaceFilter(torch.nn.Module):
     """
     ``irfftn(rfftn(mesh) * kernel(k^2))`` on a real-space mesh (reference:
@@ -597,13 +611,7 @@ class KSpaceFilter(torch.nn.Module):
         scale = self._scale(ns)
         if not mesh_values.is_cuda:           # device dispatch: CPU tensors use torch.fft with the filter table
             result = _cpu.kfilter(mesh_values, self._kfilter.to(mesh_values.dtype), scale)
-            if _nan_check and torch.isnan(result).any():
-                raise ValueError(
-                    "NaNs detected in the k-space filter result. This are probably caused "
-                    "by an unsuitable `mesh_spacing`, resulting in a problematic grid of "
-                    f"shape: {list(mesh_values.shape)}. Try adjsuting the grid by using a "
-                    "different `mesh_spacing` value."
-                )
+            check_filter_result(result)
             return result
         if self._wants_table():
             table = self._kfilter.to(mesh_values.dtype)
@@ -613,14 +621,7 @@ class KSpaceFilter(torch.nn.Module):
             cfg = _FilterConfig(dict(recip=geom.recip, spacing=geom.spacing(ns), p3m_nodes=self._p3m_nodes(),
                                      **self._p3m_mode(), **self.kernel._native_filter()), scale)
             result = _KFilter.apply(mesh_values, None, cfg)
-        if _nan_check and not torch.cuda.is_current_stream_capturing():
-            if torch.isnan(result).any():
-                raise ValueError(
-                    "NaNs detected in the k-space filter result. This are probably caused "
-                    "by an unsuitable `mesh_spacing`, resulting in a problematic grid of "
-                    f"shape: {list(mesh_values.shape)}. Try adjsuting the grid by using a "
-                    "different `mesh_spacing` value."
-                )
+        check_filter_result(result)
         return result
 
 
