@@ -69,6 +69,43 @@ struct RemoteStore {
   int64_t sA, sB, sL, off;
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The mesh pipeline is a chain of 6-8 short dependent kernels per pass.  Launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization a kernel may become resident while its predecessor is
+// still running: everything it does before pdl_wait() (shared-memory zeroing, twiddle / Green axis tables,
+// mbarrier set-up -- nothing that reads memory written by a kernel of the chain) overlaps the predecessor's
+// tail; pdl_wait() returns once the predecessor has completed and its writes are visible.  Every CTA of every
+// kernel of the chain executes pdl_wait() before it exits, so "predecessor complete" implies "everything
+// upstream complete".  pdl_trigger() at the top of a kernel lets its successor be scheduled as soon as all
+// CTAs of this kernel have started.  Without the launch attribute both are no-ops.  TPME_PDL=0 switches
+// the attribute off, TPME_PDL=all asks for it in fp32 too.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+bool pdl_everywhere();
+template <typename T> inline bool pdl_for() { return sizeof(T) == 8 || pdl_everywhere(); }
+
+// `overlap`: ask for the programmatic dependency.  Measured on B200 (profiles/r02_summary.md section 10): it pays
+// for the fp64 kernels, whose prologues (double-precision twiddles, Green axis tables) are expensive -- c3
+// 0.308 -> 0.297 ms -- and costs a little for the fp32 ones (c2 +10 %, c4 +2 %), so the callers pass
+// sizeof(T) == 8.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              bool overlap, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (overlap && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms() {
   static int cached = 0;
   if (!cached) {

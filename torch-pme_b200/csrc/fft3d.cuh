@@ -267,6 +267,7 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
       base[(int64_t)line * ls + c] = v;
   };
 
+  pdl_trigger();
   if (NG > 1) fill_twiddles<T, N>(tw, tid, nt);
   if (MODE == 2 && GV != GV_GENERIC) {
     for (int i = tid; i < N + cols; i += nt) {
@@ -275,6 +276,7 @@ lines_fft_kernel(C2<T>* __restrict__ data, int n_inner, int zc, int n_chunks, in
     }
   }
   if (NG > 1 || MODE == 2) __syncthreads();
+  pdl_wait();      // twiddles and Green axis tables above overlap the tail of the pass before
 
   // ---- first group: global -> registers ------------------------------------------------
   if (MODE == 0 || MODE == 2) {
@@ -437,8 +439,10 @@ rows_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int64_t n_row
   const int tid = threadIdx.x, nt = blockDim.x;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int rows = (int)min((int64_t)rows_per_cta, n_rows - row0);
+  pdl_trigger();
   fill_twiddles<T, NZ>(tw, tid, nt);
   __syncthreads();
+  pdl_wait();      // the twiddles above overlap the tail of the kernel before
   const C2<T>* in2 = reinterpret_cast<const C2<T>*>(in) + row0 * H;   // z[m] = x[2m] + i x[2m+1]
   for (int w = tid; w < rows * QA; w += nt) {
     const int r = w / QA, j0 = w - r * QA;
@@ -514,8 +518,10 @@ rows_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int64_t n_row
   const int tid = threadIdx.x, nt = blockDim.x;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
   const int rows = (int)min((int64_t)rows_per_cta, n_rows - row0);
+  pdl_trigger();
   fill_twiddles<T, NZ>(tw, tid, nt);
   __syncthreads();
+  pdl_wait();      // the twiddles above overlap the tail of the kernel before
   // un-split straight from global memory (natural order in buf2):
   //   Z'[k] = (X[k] + conj X[H-k]) + i conj(w^k) (X[k] - conj X[H-k])
   const C2<T>* src = in + row0 * P;
@@ -622,9 +628,11 @@ plane_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int rows_per
   C2<T>* twz = buf1 + (CZ::NG == 2 ? (size_t)rows_per_chunk * P1 : 0);
   C2<T>* twy = twz + NZ / 2;
   const int tid = threadIdx.x, nt = blockDim.x;
+  pdl_trigger();
   fill_twiddles<T, NZ>(twz, tid, nt);
   fill_twiddles<T, NY>(twy, tid, nt);
   __syncthreads();
+  pdl_wait();      // the twiddles above overlap the tail of the kernel before
   const C2<T>* in2 = reinterpret_cast<const C2<T>*>(in) + (int64_t)blockIdx.x * NY * H;
   // ---- z pass (packed half-length DIF, natural order into the plane) -----------------------
   constexpr int QAz = H / CZ::RA;
@@ -730,9 +738,11 @@ plane_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int rows_per
   C2<T>* twz = buf1 + (CZ::NG == 2 ? (size_t)rows_per_chunk * P1 : 0);
   C2<T>* twy = twz + NZ / 2;
   const int tid = threadIdx.x, nt = blockDim.x;
+  pdl_trigger();
   fill_twiddles<T, NZ>(twz, tid, nt);
   fill_twiddles<T, NY>(twy, tid, nt);
   __syncthreads();
+  pdl_wait();      // the twiddles above overlap the tail of the kernel before
   const C2<T>* src = in + (int64_t)blockIdx.x * NY * P;
   // ---- y pass (DIT along the columns; bit-reversed line order read straight from global) ----
   constexpr int RLy = CY::RL, QAy = NY / CY::RA;
@@ -850,9 +860,11 @@ plane2_r2c_kernel(const T* __restrict__ in, C2<T>* __restrict__ out, int rows_pe
   const int plane_id = blockIdx.x >> 1;
   C2<T>* other = cluster.map_shared_rank(plane, half ^ 1);
   const int tid = threadIdx.x, nt = blockDim.x;
+  pdl_trigger();
   fill_twiddles<T, NZ>(twz, tid, nt);
   fill_twiddles<T, NY>(twy, tid, nt);
   __syncthreads();
+  pdl_wait();      // the twiddles above overlap the tail of the kernel before
   const C2<T>* in2 = reinterpret_cast<const C2<T>*>(in) + ((int64_t)plane_id * NY + half * RLOC) * H;
   // ---- z pass of the local rows (packed half-length DIF, natural order into the plane) --------
   constexpr int QAz = H / CZ::RA, RL = CZ::RL;
@@ -959,9 +971,11 @@ plane2_c2r_kernel(const C2<T>* __restrict__ in, T* __restrict__ out, int rows_pe
   const int plane_id = blockIdx.x >> 1;
   C2<T>* other = cluster.map_shared_rank(plane, half ^ 1);
   const int tid = threadIdx.x, nt = blockDim.x;
+  pdl_trigger();
   fill_twiddles<T, NZ>(twz, tid, nt);
   fill_twiddles<T, NY>(twy, tid, nt);
   __syncthreads();
+  pdl_wait();      // the twiddles above overlap the tail of the kernel before
   const C2<T>* src = in + (int64_t)plane_id * NY * P;
   // ---- y pass, contiguous DIT group into the local rows (bit-reversed row order read from global) ----
   constexpr int RLy = CY::RL, QAy = NY / CY::RA, RA = CY::RA;
@@ -1077,10 +1091,10 @@ int launch_rows(bool forward, const void* in, void* out, int64_t n_rows, cudaStr
   const size_t smem = ((size_t)rows * (P + (Chain<H>::NG == 2 ? H + (H >> 4) + 1 : 0)) + NZ / 2) * sizeof(C2<T>);
   if (forward) {
     if (int rc = allow_smem(rows_r2c_kernel<T, NZ>, smem)) return rc;
-    rows_r2c_kernel<T, NZ><<<(unsigned)grid, threads, smem, s>>>((const T*)in, (C2<T>*)out, n_rows, rows);
+    TPME_CUDA_OK(launch_pdl(rows_r2c_kernel<T, NZ>, dim3((unsigned)grid), dim3(threads), smem, s, pdl_for<T>(), (const T*)in, (C2<T>*)out, n_rows, rows));
   } else {
     if (int rc = allow_smem(rows_c2r_kernel<T, NZ>, smem)) return rc;
-    rows_c2r_kernel<T, NZ><<<(unsigned)grid, threads, smem, s>>>((const C2<T>*)in, (T*)out, n_rows, rows);
+    TPME_CUDA_OK(launch_pdl(rows_c2r_kernel<T, NZ>, dim3((unsigned)grid), dim3(threads), smem, s, pdl_for<T>(), (const C2<T>*)in, (T*)out, n_rows, rows));
   }
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1131,9 +1145,8 @@ int launch_lines(void* data, int n_outer, int n_inner, int64_t ls, int d1, int64
     kernel = lines_fft_kernel<T, GT, N, MODE, GV, (MODE != 1)>;
   }
   if (int rc = allow_smem(kernel, smem)) return rc;
-  kernel<<<(unsigned)(n_outer * n_chunks), threads, smem, s>>>(
-      (C2<T>*)data, n_inner, zc, n_chunks, ls, d1, s1, s0, green, nx, ny, nz, (T*)dc_out, y_off, remote);
-  TPME_CUDA_OK(cudaGetLastError());
+  TPME_CUDA_OK(launch_pdl(kernel, dim3((unsigned)(n_outer * n_chunks)), dim3(threads), smem, s, pdl_for<T>(),
+      (C2<T>*)data, n_inner, zc, n_chunks, ls, d1, s1, s0, green, nx, ny, nz, (T*)dc_out, y_off, remote));
   return 0;
 }
 
@@ -1173,10 +1186,10 @@ int launch_plane(bool forward, const void* in, void* out, int n_planes, cudaStre
   if (smem > 216 * 1024) return -1;
   if (forward) {
     if (int rc = allow_smem(plane_r2c_kernel<T, NY, NZ>, smem)) return rc;
-    plane_r2c_kernel<T, NY, NZ><<<n_planes, threads, smem, s>>>((const T*)in, (C2<T>*)out, rows);
+    TPME_CUDA_OK(launch_pdl(plane_r2c_kernel<T, NY, NZ>, dim3(n_planes), dim3(threads), smem, s, pdl_for<T>(), (const T*)in, (C2<T>*)out, rows));
   } else {
     if (int rc = allow_smem(plane_c2r_kernel<T, NY, NZ>, smem)) return rc;
-    plane_c2r_kernel<T, NY, NZ><<<n_planes, threads, smem, s>>>((const C2<T>*)in, (T*)out, rows);
+    TPME_CUDA_OK(launch_pdl(plane_c2r_kernel<T, NY, NZ>, dim3(n_planes), dim3(threads), smem, s, pdl_for<T>(), (const C2<T>*)in, (T*)out, rows));
   }
   TPME_CUDA_OK(cudaGetLastError());
   return 0;

@@ -31,6 +31,8 @@ exclusive_scan_kernel(const int* __restrict__ in, OutT* __restrict__ out, int64_
   __shared__ int s_tile;
   __shared__ long long s_warp[kScanThreads / 32];
   __shared__ long long s_prefix;
+  pdl_trigger();
+  pdl_wait();                                  // the counters come from the kernel before
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(&state[0], 1ull);
   __syncthreads();
   const int tile = s_tile;
@@ -103,14 +105,14 @@ exclusive_scan_kernel(const int* __restrict__ in, OutT* __restrict__ out, int64_
 // `state_is_zero`: the caller has zeroed the scratch already (e.g. together with the counters, one memset)
 template <typename OutT>
 inline cudaError_t launch_exclusive_scan(const int* in, OutT* out, int64_t n, void* state, cudaStream_t s,
-                                         bool state_is_zero = false) {
+                                         bool state_is_zero = false, bool overlap = false) {
   if (n <= 0) return cudaMemsetAsync(out, 0, sizeof(OutT), s);
   if (!state_is_zero) {
     cudaError_t err = cudaMemsetAsync(state, 0, sizeof(unsigned long long) * (size_t)scan_state_words(n), s);
     if (err != cudaSuccess) return err;
   }
-  exclusive_scan_kernel<OutT><<<(unsigned)scan_tiles(n), kScanThreads, 0, s>>>(in, out, n, (unsigned long long*)state);
-  return cudaGetLastError();
+  return launch_pdl(exclusive_scan_kernel<OutT>, dim3((unsigned)scan_tiles(n)), dim3(kScanThreads), 0, s, overlap, in, out, n,
+                    (unsigned long long*)state);
 }
 
 }  // namespace tpme

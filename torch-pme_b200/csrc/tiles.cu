@@ -131,6 +131,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 tile_count_kernel(const T* __restrict__ positions, int64_t n_points, Mat3<T> r2u, MeshDims<T> dims,
                   TileGeom g, int* __restrict__ counts, int2* __restrict__ key_rank) {
+  pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
   int first[3];
@@ -145,11 +146,13 @@ __global__ void __launch_bounds__(256)
 tile_fill_kernel(const T* __restrict__ positions, int64_t n_points, Mat3<T> r2u, MeshDims<T> dims,
                  TileGeom g, const int* __restrict__ start, const int2* __restrict__ key_rank,
                  T* __restrict__ sorted_rec, int* __restrict__ sorted_idx) {
+  pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int first[3] = {0, 0, 0};
+  T x[3] = {T(0), T(0), T(0)};
+  if (i < n_points) point_first<T>(positions + 3 * i, r2u, dims, g.nodes, first, x);   // not from the chain
+  pdl_wait();                                   // bin starts (scan) and ranks (count) are
   if (i >= n_points) return;
-  int first[3];
-  T x[3];
-  point_first<T>(positions + 3 * i, r2u, dims, g.nodes, first, x);
   const int2 kr = key_rank[i];
   const int slot = start[kr.x] + kr.y;
   const int lx = first[0] & ((1 << g.tx_shift) - 1), ly = first[1] & ((1 << g.ty_shift) - 1);
@@ -219,8 +222,19 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
   // per-warp staging area: `batch` atoms x 13 words (12 one-dimensional weights + tile offset)
   T* st_rec = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ctrl) + 256) + (threadIdx.x >> 5) * (kStageWords * batch);
 
+  pdl_trigger();
   const int pencil = blockIdx.x / g.nzt, zt = blockIdx.x - pencil * g.nzt;
   const int bin0 = pencil * g.nzc + zt * g.nzc_t;
+  // The chunk starts are parked in the staging areas of the warps when they fit there (else in the not yet
+  // used tile): the tile can then be zeroed BEFORE the wait, under the tail of the kernel before.
+  const int n_warps_all = blockDim.x >> 5;
+  const bool cs_in_stage = (size_t)(g.nzc_t + 1) * sizeof(int) <= (size_t)n_warps_all * kStageWords * batch * sizeof(T);
+  if (cs_in_stage) {
+    const int n16 = (int)((size_t)tile_elems * sizeof(T) / 16);
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    for (int k = threadIdx.x; k < n16; k += blockDim.x) t4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  pdl_wait();                                   // sorted atoms / zeroed mesh: written by the kernels before
   const int p_begin = bin_start[bin0], p_end = bin_start[bin0 + g.nzc_t];
   if (p_begin == p_end) return;                 // nothing lands here: the mesh was zeroed by the caller
   const int px = pencil / g.npy, py = pencil - px * g.npy;
@@ -240,7 +254,8 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
   const int n_warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
   int s1, mid, e2;
   {
-    int* cs = reinterpret_cast<int*>(tile);          // chunk starts, parked in the (not yet used) tile
+    int* cs = cs_in_stage ? reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ctrl) + 256)
+                          : reinterpret_cast<int*>(tile);   // chunk starts
     for (int k = threadIdx.x; k <= g.nzc_t; k += blockDim.x) cs[k] = bin_start[bin0 + k];
     __syncthreads();
     if (warp == 0) {
@@ -270,7 +285,7 @@ tile_spread4_kernel(const T* __restrict__ sorted_rec, const int* __restrict__ so
 
   for (int ch = 0; ch < n_channels; ++ch) {
     // zero the tile (16-byte stores; the strides are multiples of 4 elements)
-    {
+    if (ch > 0 || !cs_in_stage) {
       const int n16 = (int)((size_t)tile_elems * sizeof(T) / 16);
       float4* t4 = reinterpret_cast<float4*>(tile);
       for (int k = threadIdx.x; k < n16; k += blockDim.x) t4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -403,8 +418,11 @@ tile_gather4_kernel(const T* __restrict__ mesh, const T* __restrict__ sorted_rec
   uint64_t* bar = reinterpret_cast<uint64_t*>(tile + tile_elems);
   __shared__ T red[9][16];
 
+  pdl_trigger();
   const int pencil = blockIdx.x / g.nzt, zt = blockIdx.x - pencil * g.nzt;
   const int bin0 = pencil * g.nzc + zt * g.nzc_t;
+  if (threadIdx.x == 0) mbar_init(bar, 1);      // set-up that overlaps the tail of the kernel before
+  pdl_wait();                                   // the mesh comes from the filter kernel before
   const int p_begin = bin_start[bin0], p_end = bin_start[bin0 + g.nzc_t];
   const bool with_r2u = (MODE & 4) && grad_r2u != nullptr;
   if (p_begin == p_end) return;
@@ -417,8 +435,7 @@ tile_gather4_kernel(const T* __restrict__ mesh, const T* __restrict__ sorted_rec
   const uint32_t main_bytes = (uint32_t)(g.tz * sizeof(T)), halo_bytes = (uint32_t)(4 * sizeof(T));
   const bool with_extra = (MODE & 4) && epi.enabled && epi.coef2 != nullptr;
 
-  if (threadIdx.x == 0) mbar_init(bar, 1);
-  __syncthreads();
+  __syncthreads();                              // the mbarrier (initialised above) is visible to all threads
   T cellsum[9];
 #pragma unroll
   for (int e = 0; e < 9; ++e) cellsum[e] = T(0);
@@ -594,10 +611,10 @@ static int launch_tile_gather(const tpme_tile_plan* plan, const void* mesh, cons
                                       max_smem_optin() - (int)attr.sharedSizeBytes));
     configured = true;
   }
-  kernel<<<(unsigned)(g.npx * g.npy * g.nzt), plan->gather_threads, smem, stream>>>(
+  TPME_CUDA_OK(launch_pdl(kernel, dim3((unsigned)(g.npx * g.npy * g.nzt)), dim3(plan->gather_threads), smem, stream, pdl_for<T>(),
       (const T*)mesh, (const T*)rec, idx, bin_start, (const T*)positions, (const T*)coef, n_channels,
       load_mat3<T>(r2u), g, (T*)values, (T*)dvalues, (T*)grad_positions, accumulate, (T*)grad_r2u, epi,
-      getenv("TPME_TILE_DEBUG") ? atoi(getenv("TPME_TILE_DEBUG")) : 0);
+      getenv("TPME_TILE_DEBUG") ? atoi(getenv("TPME_TILE_DEBUG")) : 0));
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -738,16 +755,17 @@ extern "C" int tpme_tile_sort(int dtype, const tpme_tile_plan* plan, const void*
       tile_count_kernel<double><<<grid, 256, 0, s>>>((const double*)positions, n_points, load_mat3<double>(r2u_host),
                                                      make_dims<double>(g.nx, g.ny, g.nz), g, bin_count, (int2*)key_rank);
   }
-  TPME_CUDA_OK(launch_exclusive_scan<int>(bin_count, bin_start, plan->n_bins, scan_state, s, true));
+  TPME_CUDA_OK(launch_exclusive_scan<int>(bin_count, bin_start, plan->n_bins, scan_state, s, true,
+                                          dtype == 1 || pdl_everywhere()));
   if (n_points > 0) {
     if (dtype == 0)
-      tile_fill_kernel<float><<<grid, 256, 0, s>>>((const float*)positions, n_points, load_mat3<float>(r2u_host),
-                                                   make_dims<float>(g.nx, g.ny, g.nz), g, bin_start,
-                                                   (const int2*)key_rank, (float*)sorted_rec, sorted_idx);
+      TPME_CUDA_OK(launch_pdl(tile_fill_kernel<float>, dim3(grid), dim3(256), 0, s, pdl_for<float>(), (const float*)positions, n_points,
+                              load_mat3<float>(r2u_host), make_dims<float>(g.nx, g.ny, g.nz), g, bin_start,
+                              (const int2*)key_rank, (float*)sorted_rec, sorted_idx));
     else
-      tile_fill_kernel<double><<<grid, 256, 0, s>>>((const double*)positions, n_points, load_mat3<double>(r2u_host),
-                                                    make_dims<double>(g.nx, g.ny, g.nz), g, bin_start,
-                                                    (const int2*)key_rank, (double*)sorted_rec, sorted_idx);
+      TPME_CUDA_OK(launch_pdl(tile_fill_kernel<double>, dim3(grid), dim3(256), 0, s, pdl_for<double>(), (const double*)positions, n_points,
+                              load_mat3<double>(r2u_host), make_dims<double>(g.nx, g.ny, g.nz), g, bin_start,
+                              (const int2*)key_rank, (double*)sorted_rec, sorted_idx));
   }
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
@@ -780,8 +798,8 @@ extern "C" int tpme_tile_spread(int dtype, const tpme_tile_plan* plan, const voi
                                         max_smem_optin()));
       configured = true;
     }
-    tile_spread4_kernel<float><<<grid, plan->spread_threads, smem, s>>>(
-        (const float*)sorted_rec, sorted_idx, bin_start, (const float*)weights, n_channels, method, g, (float*)mesh, plan->spread_batch, dbg);
+    TPME_CUDA_OK(launch_pdl(tile_spread4_kernel<float>, dim3(grid), dim3(plan->spread_threads), smem, s, pdl_for<float>(),
+        (const float*)sorted_rec, sorted_idx, bin_start, (const float*)weights, n_channels, method, g, (float*)mesh, plan->spread_batch, dbg));
   } else {
     static thread_local bool configured = false;
     if (!configured) {
@@ -789,8 +807,8 @@ extern "C" int tpme_tile_spread(int dtype, const tpme_tile_plan* plan, const voi
                                         max_smem_optin()));
       configured = true;
     }
-    tile_spread4_kernel<double><<<grid, plan->spread_threads, smem, s>>>(
-        (const double*)sorted_rec, sorted_idx, bin_start, (const double*)weights, n_channels, method, g, (double*)mesh, plan->spread_batch, dbg);
+    TPME_CUDA_OK(launch_pdl(tile_spread4_kernel<double>, dim3(grid), dim3(plan->spread_threads), smem, s, pdl_for<double>(),
+        (const double*)sorted_rec, sorted_idx, bin_start, (const double*)weights, n_channels, method, g, (double*)mesh, plan->spread_batch, dbg));
   }
   TPME_CUDA_OK(cudaGetLastError());
   return 0;
