@@ -152,3 +152,40 @@ def test_full_size_against_oracle(name, order):
     assert eV < tol and ed < tol
     assert err[keep].max() / fmax < tol
     assert l2 < (tol if keep.all() else 2e-2)
+
+
+@pytest.mark.parametrize("n_side, n_mesh, dtype", [(8, 16, torch.float64), (20, 64, torch.float32),
+                                                    (32, 64, torch.float64)])
+def test_prezeroed_meshes_equal_inline_fill(n_side, n_mesh, dtype, monkeypatch):
+    """
+    The fused node zero-fills the meshes of its two spreads on a branch of their own
+    (`calculators._zeroed_meshes`): same numbers as the fill inside the spread entry points, a second backward
+    through the same node (the pre-filled mesh is gone by then) gives the same gradients, and no_grad works.
+    """
+    import torchpme_b200 as tp
+    from torchpme_b200 import calculators
+
+    pos, q, cell, idx, d = rocksalt(n_side, dtype=dtype, device="cuda")
+    mesh_spacing = float(cell[0, 0]) / (n_mesh / 2 - 2)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=1.2).to("cuda"), mesh_spacing=mesh_spacing)
+
+    def run():
+        p = pos.clone().requires_grad_(True)
+        qq = q.clone().requires_grad_(True)
+        V = calc(qq, cell, p, idx, d)
+        loss = (V * V).sum()
+        g1 = torch.autograd.grad(loss, (p, qq), retain_graph=True)
+        g2 = torch.autograd.grad(loss, (p, qq))
+        with torch.no_grad():
+            V0 = calc(q, cell, pos, idx, d)
+        return V.detach(), g1, g2, V0
+
+    monkeypatch.setattr(calculators, "_PREZERO", True)
+    Va, g1a, g2a, V0a = run()
+    monkeypatch.setattr(calculators, "_PREZERO", False)
+    Vb, g1b, g2b, V0b = run()
+    tol = 1e-12 if dtype == torch.float64 else 1e-5       # fp32 direct spread: unordered atomics
+    assert rel_err(Va, Vb) < tol and rel_err(V0a, Vb) < tol and rel_err(V0b, Vb) < tol
+    for a, b, c in zip(g1a, g2a, g1b):
+        assert rel_err(a, c) < tol
+        assert rel_err(b, c) < tol

@@ -347,7 +347,8 @@ def tile_sort(positions, r2u, ns, nodes: int, method: int):
     return TileSort(plan, positions, r2u) if plan is not None else None
 
 
-def tile_spread(tiles: TileSort, weights, method: int, out=None):
+def tile_spread(tiles: TileSort, weights, method: int, out=None, accumulate=False):
+    """`accumulate`: `out` already holds what the spread is added to (e.g. zeros written off the critical path)"""
     lib = load()
     n, c = weights.shape
     plan = tiles.plan
@@ -356,8 +357,8 @@ def tile_spread(tiles: TileSort, weights, method: int, out=None):
     with _on(weights, "particle_weights"):
         _check(lib.tpme_tile_spread(_dtype_id(weights), ctypes.byref(plan), _dev(tiles.rec, "sorted_rec"),
                                     _dev(tiles.idx, "sorted_idx"), _dev(tiles.bin_start, "bin_start"),
-                                    _dev(weights, "particle_weights"), n, c, method, _dev(out, "mesh"), 0,
-                                    _stream()), "tpme_tile_spread")
+                                    _dev(weights, "particle_weights"), n, c, method, _dev(out, "mesh"),
+                                    int(accumulate and out is not None), _stream()), "tpme_tile_spread")
     _count()
     return out
 
@@ -380,15 +381,16 @@ def tile_gather(tiles: TileSort, mesh, method: int, values=None, dvalues=None, g
 
 
 def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=None, point_list=None,
-           tiles: TileSort | None = None):
+           tiles: TileSort | None = None, accumulate=False):
     """
+    `accumulate` (with `out`): add to `out` instead of zero-filling it first;
     `slab` = (x0, nx_local): spread into the local x slab (C, nx_local, ny, nz) only;
     `point_list` = result of :func:`slab_select_points` for that slab;
     `tiles` = :class:`TileSort` of `positions`: use the tiled kernel
     """
     if tiles is not None and slab is None:
         if tiles.spread_tiled:
-            return tile_spread(tiles, weights, method, out=out)
+            return tile_spread(tiles, weights, method, out=out, accumulate=accumulate)
     lib = load()
     n, c = weights.shape
     nx, ny, nz = ns
@@ -398,8 +400,8 @@ def spread(positions, weights, r2u, ns, nodes: int, method: int, out=None, slab=
     with _on(positions, "positions"):
         _check(lib.tpme_spread_slab(_dtype_id(positions), _dev(positions, "positions"),
                                     _dev(weights, "particle_weights"), n, c, _mat9(r2u), nx, ny, nz,
-                                    x0, nxl, *_list_args(point_list), nodes, method, _dev(out, "mesh"), 0,
-                                    _stream()),
+                                    x0, nxl, *_list_args(point_list), nodes, method, _dev(out, "mesh"),
+                                    int(accumulate), _stream()),
                "tpme_spread")
     _count()
     return out

@@ -9,6 +9,7 @@ CPU path (a CPU tensor raises ``NativeLibraryError``).
 
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Optional
 
@@ -93,6 +94,43 @@ def _side_stream(device) -> "torch.cuda.Stream":
     return stream
 
 
+_zero_streams: dict = {}
+# TPME_PREZERO=0: the spreads zero-fill their mesh themselves, on the critical path (A/B switch)
+_PREZERO = os.environ.get("TPME_PREZERO", "1") != "0"
+
+
+def _zeroed_meshes(like, n_channels: int, ns, count: int, branch: bool = True):
+    """
+    `count` zero-filled (C, nx, ny, nz) meshes for the spreads of one fused step.  The fills run on their own
+    stream -- a parallel branch of a captured graph -- next to the tile sort instead of between the sort and
+    the spread (c3: two 16.8 MB fills, ~10 us each, leave the mesh chain); the caller's stream joins that
+    branch in :func:`_join_zeroed` right before the first spread.  The mesh of the backward spread is
+    filled here as well, so the backward pass starts with its spread.
+    """
+    dev = like.device
+    shape = (n_channels, int(ns[0]), int(ns[1]), int(ns[2]))
+    meshes = [torch.empty(shape, dtype=like.dtype, device=dev) for _ in range(count)]
+    if not (_PREZERO and branch):
+        return meshes, None
+    key = torch.device(dev).index
+    stream = _zero_streams.get(key)
+    if stream is None:
+        stream = _zero_streams[key] = torch.cuda.Stream(device=dev)
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream):
+        for m in meshes:
+            m.zero_()
+    return meshes, stream
+
+
+def _join_zeroed(device, stream) -> bool:
+    """the caller's stream waits for the fills; returns whether the meshes are zero (spread with accumulate)"""
+    if stream is None:
+        return False
+    torch.cuda.current_stream(device).wait_stream(stream)
+    return True
+
+
 class _FusedStepConfig:
     """by-value launch parameters of one fused PME / P3M evaluation"""
     __slots__ = ("r2u", "ns", "nodes", "method", "green_args", "pair_pot", "full_list",
@@ -146,10 +184,17 @@ class _FusedMeshPotential(torch.autograd.Function):
             _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=pair_out)
         if defer:
             out.zero_()
+        # the meshes of this spread and of the backward one are zero-filled on a branch of their own
+        # (not with deferred joins: there the mesh chain hides behind the pair-list copy, nothing to gain)
+        n_spreads = 2 if (ctx.needs_input_grad[0] or need_pos) and not defer else 1
+        meshes, zs = _zeroed_meshes(q, q.shape[1], cfg.ns, n_spreads, branch=not defer)
         # atoms binned by mesh tile once per step: the spread, the gather and both backward launches
         # stage their pencil of the mesh in shared memory (csrc/tiles.cu); None = direct kernels
         tiles = _native.tile_sort(pos, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
-        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
+        zeroed = _join_zeroed(q.device, zs)
+        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles, out=meshes[0],
+                             accumulate=zeroed)
+        ctx.zero_mesh = meshes[1] if zeroed and len(meshes) > 1 else None
         green = _native.make_green(scale=1.0, **cfg.green_args)
         phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
         check_filter_result(phi)      # the reference's NaN guard (a host sync; see mesh.set_nan_check)
@@ -202,7 +247,9 @@ class _FusedMeshPotential(torch.autograd.Function):
                                                     _native.pair_count_of(idx), g_pos4, None)
         g_pos = None
         if need_q or need_pos:
-            rho_g = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
+            zero_mesh, ctx.zero_mesh = ctx.zero_mesh, None       # filled during forward; good for one backward
+            rho_g = _native.spread(pos, g, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles, out=zero_mesh,
+                                   accumulate=zero_mesh is not None)
             green = _native.make_green(scale=1.0, **cfg.green_args)
             psi, _, dc_g = _native.kfilter_apply(rho_g, green, want_dc=True)
             if forked and need_q:
@@ -448,8 +495,11 @@ class PMECalculator(Calculator):
             _native.pair_forward(q, idx, d, None, mask_u8, cfg.full_list, cfg.pair_pot, out=out)
             _native.pair_backward(q, idx, d, None, mask_u8, q, cfg.full_list, cfg.pair_pot,
                                   want_charges=False, want_pairs=True, grad_pairs_out=g_d)
+        meshes, zs = _zeroed_meshes(q, q.shape[1], cfg.ns, 1)
         tiles = _native.tile_sort(pos, cfg.r2u, cfg.ns, cfg.nodes, cfg.method)
-        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles)
+        zeroed = _join_zeroed(q.device, zs)
+        rho = _native.spread(pos, q, cfg.r2u, cfg.ns, cfg.nodes, cfg.method, tiles=tiles, out=meshes[0],
+                             accumulate=zeroed)
         green = _native.make_green(scale=1.0, **cfg.green_args)
         phi, _, dc = _native.kfilter_apply(rho, green, want_dc=True)
         main.wait_stream(side)
