@@ -20,10 +20,27 @@ charges) overlaps it; one ``replay()`` + ``synchronize()`` is a complete host-to
 
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import mesh as _mesh
 from .mesh import set_nan_check
+
+
+def _capture_stream(dev, dtype, calculator=None) -> "torch.cuda.Stream":
+    """
+    The stream a step is captured on carries the mesh chain, the critical path of the step; the pair kernels of
+    the real-space branch (side stream) fill the GPU for 40-100 us each while the short mesh kernels wait for
+    CTA slots.  TPME_GRAPH_PRIORITY=1 captures on a high-priority stream, which gives the kernel nodes of the mesh
+    chain a higher launch priority than the branch kernels.  Opt-in, because the measured effect depends on the
+    workload (profiles/r02_summary.md section 12): c5 0.268 -> 0.250 ms, c2 unchanged, c3 0.290 -> 0.293 ms,
+    c4 0.836 -> 0.850 ms.  Never applied to a slab-decomposed calculator (its exchange / barrier kernels keep the
+    stream layout they were validated with).
+    """
+    slab = getattr(calculator, "_slab_cfg", None) is not None or hasattr(calculator, "transport")
+    high = os.environ.get("TPME_GRAPH_PRIORITY", "0") == "1" and not slab
+    return torch.cuda.Stream(device=dev, priority=-1 if high else 0)
 
 
 class GraphedStep:
@@ -35,7 +52,7 @@ class GraphedStep:
         if dev.type != "cuda":
             raise ValueError("GraphedStep needs CUDA tensors")
         self.calculator = calculator
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = _capture_stream(dev, positions.dtype, calculator)
         self.aux = torch.cuda.Stream(device=dev)     # side branch of the energy reduction
         self.graph = torch.cuda.CUDAGraph()
         self.stream.wait_stream(torch.cuda.current_stream(dev))
@@ -198,7 +215,7 @@ class GraphedPositionsStep:
             exact = neighbor_list(positions, cell, cutoff, full_neighbor_list=full, index_dtype=index_dtype)[0].shape[0]
             capacity = int(1.2 * exact) + 1024
         self.calculator, self.cutoff, self.capacity = calculator, float(cutoff), int(capacity)
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = _capture_stream(dev, positions.dtype, calculator)
         self.aux = torch.cuda.Stream(device=dev)
         self.graph = torch.cuda.CUDAGraph()
         self.stream.wait_stream(torch.cuda.current_stream(dev))
