@@ -4,6 +4,7 @@ round 2 and are part of the default GPU suite since): the one-filter-pass energy
 the device-built neighbor list feeding the calculators, and the spline / combined potentials through
 the generic table and per-pair-value routes.
 """
+import numpy as np
 import pytest
 import torch
 
@@ -254,5 +255,38 @@ def test_nan_guard_on_the_fused_path():
     tp.set_nan_check(False)
     try:
         assert torch.isnan(calc(bad, cell, pos, idx, d)).any()
+    finally:
+        tp.set_nan_check(True)
+
+
+def test_device_cell_step_has_no_host_sync():
+    """
+    A step with a NEW cell tensor made by `device_cell` (geometry registered from the host values) runs without
+    any host synchronisation: forward + backward under torch's sync-debug "error" mode.
+    """
+    import torchpme_b200 as tp
+    from helpers import rocksalt
+
+    pos, q, cell, idx, d = rocksalt(8, dtype=torch.float32, device="cuda")
+    mesh_spacing = float(cell[0, 0]) / (16 / 2 - 2)
+    calc = tp.PMECalculator(tp.CoulombPotential(smearing=1.2).to("cuda"), mesh_spacing=mesh_spacing)
+    box = cell.cpu().numpy().astype(np.float64)
+    tp.set_nan_check(False)          # the reference's NaN guard on the filtered mesh is a host read by design
+    try:
+        p = pos.clone().requires_grad_(True)
+        V0 = calc(q, cell, p, idx, d)
+        (V0 * q).sum().backward()     # warm: plans, allocator
+        torch.cuda.synchronize()
+        torch.cuda.set_sync_debug_mode("error")
+        try:
+            cell2 = tp.device_cell(box * 1.0005, "cuda", torch.float32)
+            p2 = pos.clone().requires_grad_(True)
+            V = calc(q, cell2, p2, idx, d)
+            (V * q).sum().backward()
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+        torch.cuda.synchronize()
+        assert torch.isfinite(V).all() and torch.isfinite(p2.grad).all()
+        assert float((V - V0).abs().max()) < 1e-2 * float(V0.abs().max())      # a 0.05 % larger box
     finally:
         tp.set_nan_check(True)

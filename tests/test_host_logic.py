@@ -192,3 +192,30 @@ def test_tuning_timings_on_cpu():
     assert isinstance(seconds, float) and 0 < seconds < 10
     with pytest.raises(ValueError):       # the reference validates the structure in the constructor
         TuningTimings(q, torch.eye(2, dtype=torch.float64), pos, idx, d)
+
+
+def test_device_cell_registers_geometry_from_host_values(monkeypatch):
+    """device_cell(): the geometry of the returned tensor comes from the host values -- geometry_of() must not
+    read the tensor back (on CUDA that read is the one stream sync of a step with a new cell)"""
+    from torchpme_b200 import mesh
+
+    rng = np.random.default_rng(11)
+    box = np.eye(3) * 9.0 + rng.uniform(-0.3, 0.3, (3, 3))
+    for dtype in (torch.float64, torch.float32):
+        cell = tp.device_cell(box, "cpu", dtype)
+        assert cell.dtype == dtype and cell.shape == (3, 3)
+        built = []
+        original = mesh.CellGeometry.__init__
+        monkeypatch.setattr(mesh.CellGeometry, "__init__", lambda self, c: (built.append(1), original(self, c))[1])
+        geom = mesh.geometry_of(cell)
+        assert not built                                          # cache hit: nothing rebuilt
+        monkeypatch.setattr(mesh.CellGeometry, "__init__", original)
+        fresh = mesh.CellGeometry(cell.clone())                   # what a device read-back would have given
+        np.testing.assert_array_equal(geom.cell, fresh.cell)
+        np.testing.assert_array_equal(np.asarray(geom.recip), np.asarray(fresh.recip))
+        assert geom.volume == fresh.volume and geom.ns_mesh(0.7) == fresh.ns_mesh(0.7)
+        cell.mul_(1.01)                                           # in-place change: the cached geometry is stale
+        assert mesh.geometry_of(cell).volume != geom.volume
+    assert tp.device_cell([[1, 0, 0], [0, 2, 0], [0, 0, 3]], "cpu").dtype == torch.get_default_dtype()
+    with pytest.raises(ValueError, match="should be of shape"):
+        tp.device_cell(np.eye(2), "cpu")

@@ -15,7 +15,7 @@ from . import calculators, graphs, lib, mesh, potentials, prefactors, tuning  # 
 from ._native import NativeLibraryError, library_path  # noqa: F401
 from .calculators import Calculator, P3MCalculator, PMECalculator
 from .graphs import GraphedPositionsStep, GraphedStep  # noqa: F401
-from .mesh import set_nan_check  # noqa: F401
+from .mesh import device_cell, set_nan_check  # noqa: F401
 from .potentials import (CombinedPotential, CoulombPotential, InversePowerLawPotential, Potential,
                          SplinePotential)
 

@@ -368,6 +368,7 @@ class PMECalculator(Calculator):
         self.mesh_spacing = mesh_spacing
         self.interpolation_nodes = interpolation_nodes
         self._fused_cfg = self._fused_key = self._fused_geom = None
+        self._fused_pot_key = self._fused_pot_terms = None
         unit = torch.eye(3, device=potential.smearing.device, dtype=potential.smearing.dtype)
         ones = torch.ones(3, dtype=torch.int64, device=unit.device)
         self.kspace_filter = self._make_filter(unit, ones)
@@ -452,8 +453,14 @@ class PMECalculator(Calculator):
             cfg.full_list = self.full_neighbor_list
             ivolume = 1.0 / geom.volume
             cfg.half_ivolume = 0.5 * ivolume
-            cfg.self_half = 0.5 * float(pot.self_contribution())
-            cfg.background_ivolume = float(pot.background_correction()) * ivolume
+            # self / background terms depend on the potential's scalars only: evaluated (on the device, by the
+            # potential's own torch code) and read back once per potential state, not once per cell
+            pot_key = (kind, exponent, smearing, prefactor)
+            if self._fused_pot_key != pot_key:
+                self._fused_pot_terms = (float(pot.self_contribution()), float(pot.background_correction()))
+                self._fused_pot_key = pot_key
+            cfg.self_half = 0.5 * self._fused_pot_terms[0]
+            cfg.background_ivolume = self._fused_pot_terms[1] * ivolume
             self._fused_cfg, self._fused_key, self._fused_geom = cfg, key, geom
         return cfg
 

@@ -68,6 +68,27 @@ def geometry_of(cell: torch.Tensor) -> CellGeometry:
     return geom
 
 
+def device_cell(cell, device, dtype: torch.dtype | None = None) -> torch.Tensor:
+    """
+    A (3, 3) cell that lives on the host (numpy array, nested list or CPU tensor) as a tensor on `device`
+    whose geometry is already in the cache, computed from the host values: the calculators then take their
+    by-value launch parameters (inverse cell, reciprocal cell, volume, mesh size) without the device -> host
+    read, i.e. without a stream synchronisation.  For drivers whose box changes every step (NPT molecular
+    dynamics): ``cell = torchpme_b200.device_cell(box, "cuda")`` instead of ``torch.tensor(box, device="cuda")``.
+    """
+    host = torch.as_tensor(cell).detach().to("cpu")
+    if host.shape != (3, 3):
+        raise ValueError(f"cell of shape {list(host.shape)} should be of shape (3, 3)")
+    if dtype is None:
+        dtype = host.dtype if host.dtype.is_floating_point else torch.get_default_dtype()
+    host = host.to(dtype).contiguous()
+    on_device = host.to(device=device, non_blocking=True) if torch.device(device).type != "cpu" else host.clone()
+    if len(_geometry_cache) > 64:
+        _geometry_cache.clear()
+    _geometry_cache[id(on_device)] = (weakref.ref(on_device), on_device._version, CellGeometry(host))
+    return on_device
+
+
 def _host_ints(t: torch.Tensor) -> tuple:
     return tuple(int(v) for v in t.detach().to("cpu").tolist())
 
