@@ -10,6 +10,14 @@
  * (plan creation excepted).  Return value: 0 on success, non-zero on failure
  * (tpme_last_error() gives the message).
  *
+ * Ordering: the calls are ordered like any other work on `stream`.  The float64 kernels
+ * of the mesh entry points (tile sort / spread / gather, FFT, filter) are launched with
+ * programmatic stream serialisation: a kernel may become resident while the kernel before
+ * it on the same stream is still running, but it touches nothing but its own shared memory
+ * and read-only inputs of the whole step until that kernel has completed
+ * (griddepcontrol.wait), so callers need no extra synchronisation.  TPME_PDL=0 in the
+ * environment turns the attribute off.
+ *
  * Conventions (same as the reference): cell rows are lattice vectors; `r2u` is the
  * 3x3 row-major matrix with u = r @ r2u = ns * (r @ cell^-1)
  * (src/torchpme/lib/mesh_interpolator.py:326); positions are (N,3) row-major,
